@@ -1,0 +1,392 @@
+// asr_aux.cu -- producers and consumers either side of the solve:
+//   asr_warp_affine         augmentation_utils.py:11-27   create_augmented_copies (rotate -> translate)
+//   asr_opm_extract         augmentation_utils.py:80-115  argmax / slice / slice_max OPM (+ utils.py:115-119)
+//   asr_minmax_normalize    superres_utils.py:56-62,186-194
+//   asr_backproject_batched superresolution.py:139-161    max_superresolution / mean_superresolution
+//   asr_threshold           superres_utils.py:118-139     threshold_image
+// Same numerical contract as the solve: un-fused fp32, TensorFlow's evaluation order.
+#include <math.h>
+#include <vector>
+
+#include "asr_common.cuh"
+
+namespace asr {
+
+// monotone float <-> uint map so that min/max reductions can use integer atomics (exact, order-free)
+__device__ __forceinline__ unsigned enc(float f) {
+    const unsigned u = __float_as_uint(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float dec(unsigned e) {
+    return __uint_as_float((e & 0x80000000u) ? (e & 0x7fffffffu) : ~e);
+}
+
+// ================================================================================================
+// K3: augmentation warp.  out[k] = translate(rotate(image, angle_k), shift_k), zero fill.
+// ================================================================================================
+// One CTA per 32x32 output tile per copy.  The translate stage reads the rotated image p only on
+// the integer window (Z+s, Z+s+1), s = floor(-d), so the CTA first evaluates p once per position of
+// the 33x33 window into shared memory (each p would otherwise be recomputed by its 4 consumers),
+// then forms the outputs with per-column/row tap tables carrying the literal translate weights.
+constexpr int K3_T = 32;
+constexpr int K3_P = K3_T + 1;
+constexpr int K3_THREADS = 256;
+constexpr int K3_CMAX = 4;
+
+struct WarpXf { float r0, r1, r2, r3, r4, r5, tx, ty; };
+
+__device__ __forceinline__ float2 warp_taps(int Z, float t, int s, int limit, int interp) {
+    const float iz = fadd((float)Z, t);
+    const int base = Z + s;
+    float wa, wb;
+    if (interp == ASR_INTERP_BILINEAR) {
+        const float f = floorf(iz);
+        const float w0 = fsub(fadd(f, 1.0f), iz), w1 = fsub(iz, f);
+        if ((int)f == base) { wa = w0; wb = w1; } else { wa = 0.0f; wb = w0; }
+    } else {  // NEAREST: std::round, half away from zero
+        const int n = (int)roundf(iz);
+        wa = (n == base) ? 1.0f : 0.0f;
+        wb = (n == base + 1) ? 1.0f : 0.0f;
+    }
+    if (base < 0 || base >= limit) wa = 0.0f;
+    if (base + 1 < 0 || base + 1 >= limit) wb = 0.0f;
+    return make_float2(wa, wb);
+}
+
+__global__ void __launch_bounds__(K3_THREADS)
+k_warp_affine(const float* __restrict__ img, const WarpXf* __restrict__ xf, float* __restrict__ out, int H, int W, int C,
+              int interp) {
+    __shared__ float p[K3_P * K3_P * K3_CMAX];
+    __shared__ float2 colw[K3_T], roww[K3_T];
+    const int k = blockIdx.y, tid = threadIdx.x;
+    const int ntx = (W + K3_T - 1) / K3_T;
+    const int X0 = (blockIdx.x % ntx) * K3_T, Y0 = (blockIdx.x / ntx) * K3_T;
+    const WarpXf T = xf[k];
+    const int sx = (int)floorf(T.tx), sy = (int)floorf(T.ty);
+    const int qx_lo = X0 + sx, qy_lo = Y0 + sy;
+
+    if (tid < K3_T) colw[tid] = warp_taps(X0 + tid, T.tx, sx, W, interp);
+    else if (tid < 2 * K3_T) roww[tid - K3_T] = warp_taps(Y0 + tid - K3_T, T.ty, sy, H, interp);
+
+    for (int e = tid; e < K3_P * K3_P; e += K3_THREADS) {
+        const int py = e / K3_P, px = e % K3_P;
+        const float qx = (float)(qx_lo + px), qy = (float)(qy_lo + py);
+        const float ix = affine_coord(T.r0, qx, T.r1, qy, T.r2), iy = affine_coord(T.r3, qx, T.r4, qy, T.r5);
+        float* dst = p + e * C;
+        if (interp == ASR_INTERP_BILINEAR) {
+            const float fx = floorf(ix), fy = floorf(iy);
+            const float wx0 = fsub(fadd(fx, 1.0f), ix), wx1 = fsub(ix, fx);
+            const float wy0 = fsub(fadd(fy, 1.0f), iy), wy1 = fsub(iy, fy);
+            const int x0 = (int)fx, y0 = (int)fy;
+            const bool vx0 = x0 >= 0 && x0 < W, vx1 = x0 + 1 >= 0 && x0 + 1 < W;
+            const bool vy0 = y0 >= 0 && y0 < H, vy1 = y0 + 1 >= 0 && y0 + 1 < H;
+            const float* b00 = img + ((size_t)y0 * W + x0) * C;
+            for (int c = 0; c < C; ++c) {
+                const float v00 = (vy0 && vx0) ? __ldg(b00 + c) : 0.0f;
+                const float v01 = (vy0 && vx1) ? __ldg(b00 + C + c) : 0.0f;
+                const float v10 = (vy1 && vx0) ? __ldg(b00 + (size_t)W * C + c) : 0.0f;
+                const float v11 = (vy1 && vx1) ? __ldg(b00 + (size_t)W * C + C + c) : 0.0f;
+                dst[c] = bilerp(v00, v01, v10, v11, wx0, wx1, wy0, wy1);
+            }
+        } else {
+            const long xn = (long)roundf(ix), yn = (long)roundf(iy);
+            const bool v = xn >= 0 && xn < W && yn >= 0 && yn < H;
+            for (int c = 0; c < C; ++c) dst[c] = v ? __ldg(img + ((size_t)yn * W + xn) * C + c) : 0.0f;
+        }
+    }
+    __syncthreads();
+
+    float* ok = out + (size_t)k * H * W * C;
+    const int row_elems = K3_T * C;
+    for (int e = tid; e < K3_T * row_elems; e += K3_THREADS) {
+        const int ty = e / row_elems, rem = e % row_elems, tx = rem / C, c = rem % C;
+        const int X = X0 + tx, Y = Y0 + ty;
+        if (X >= W || Y >= H) continue;
+        const float2 wc = colw[tx], wr = roww[ty];
+        const float* p00 = p + (ty * K3_P + tx) * C + c;
+        float v;
+        if (interp == ASR_INTERP_BILINEAR) {
+            v = bilerp(p00[0], p00[C], p00[K3_P * C], p00[K3_P * C + C], wc.x, wc.y, wr.x, wr.y);
+        } else {   // exactly one tap has weight 1 (or none: zero fill)
+            const float a = (wc.x != 0.0f) ? p00[0] : ((wc.y != 0.0f) ? p00[C] : 0.0f);
+            const float bq = (wc.x != 0.0f) ? p00[K3_P * C] : ((wc.y != 0.0f) ? p00[K3_P * C + C] : 0.0f);
+            v = (wr.x != 0.0f) ? a : ((wr.y != 0.0f) ? bq : 0.0f);
+        }
+        ok[((size_t)Y * W + X) * C + c] = v;
+    }
+}
+
+// ================================================================================================
+// K4: OPM extraction from NHWC logits
+// ================================================================================================
+constexpr int K4_THREADS = 256;
+constexpr int K4_KMAX = 64;
+
+// per-copy min / max over all K channels (slice mode, augmentation_utils.py:100-101)
+__global__ void k_copy_minmax(const float* __restrict__ logits, size_t per_copy, unsigned* __restrict__ mm) {
+    const int n = blockIdx.y;
+    const float* p = logits + (size_t)n * per_copy;
+    float lo = INFINITY, hi = -INFINITY;
+    const size_t n4 = per_copy / 4;
+    const float4* p4 = reinterpret_cast<const float4*>(p);
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+        const float4 v = __ldg(p4 + i);
+        lo = fminf(fminf(lo, fminf(v.x, v.y)), fminf(v.z, v.w));
+        hi = fmaxf(fmaxf(hi, fmaxf(v.x, v.y)), fmaxf(v.z, v.w));
+    }
+    for (size_t i = n4 * 4 + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < per_copy; i += (size_t)gridDim.x * blockDim.x) {
+        lo = fminf(lo, p[i]); hi = fmaxf(hi, p[i]);
+    }
+    lo = warp_min(lo); hi = warp_max(hi);
+    if ((threadIdx.x & 31) == 0) { atomicMin(mm + 2 * n, enc(lo)); atomicMax(mm + 2 * n + 1, enc(hi)); }
+}
+
+__global__ void k_mm_init(unsigned* mm, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) { mm[2 * i] = 0xffffffffu; mm[2 * i + 1] = 0u; }
+}
+
+// pixels are staged through shared memory so that global reads are fully coalesced float4 streams;
+// each thread then scans its pixel's K channels at stride K (odd K -> conflict-free)
+__global__ void __launch_bounds__(K4_THREADS)
+k_opm_extract(const float* __restrict__ logits, int K, size_t px_per_copy, int class_id, int mode,
+              const unsigned* __restrict__ mm, float* __restrict__ class_out, float* __restrict__ max_out) {
+    extern __shared__ __align__(16) float sm[];   // [K4_THREADS * K]
+    const int n = blockIdx.y;
+    const size_t px0 = (size_t)blockIdx.x * K4_THREADS;
+    const size_t npx = min((size_t)K4_THREADS, px_per_copy - px0);
+    const float* src = logits + ((size_t)n * px_per_copy + px0) * K;
+    const size_t nel = npx * K;
+    if ((((uintptr_t)src) & 15) == 0) {
+        const float4* s4 = reinterpret_cast<const float4*>(src);
+        float4* d4 = reinterpret_cast<float4*>(sm);
+        for (size_t i = threadIdx.x; i < nel / 4; i += K4_THREADS) d4[i] = __ldg(s4 + i);
+        for (size_t i = (nel / 4) * 4 + threadIdx.x; i < nel; i += K4_THREADS) sm[i] = __ldg(src + i);
+    } else {
+        for (size_t i = threadIdx.x; i < nel; i += K4_THREADS) sm[i] = __ldg(src + i);
+    }
+    __syncthreads();
+    if (threadIdx.x >= npx) return;
+    const float* v = sm + threadIdx.x * K;
+    const size_t o = (size_t)n * px_per_copy + px0 + threadIdx.x;
+    if (mode == ASR_OPM_ARGMAX) {
+        int best = 0;
+        float bv = v[0];
+        for (int k = 1; k < K; ++k) { const float t = v[k]; if (t > bv) { bv = t; best = k; } }   // ties -> lowest index
+        class_out[o] = (best == class_id) ? (float)class_id : 0.0f;
+    } else if (mode == ASR_OPM_SLICE) {
+        const float mn = dec(mm[2 * n]), mx = dec(mm[2 * n + 1]);
+        const float den = (fsub(mx, mn) != 0.0f) ? fsub(mx, mn) : 1.0f;
+        const float num = fmul(fsub(v[class_id], mn), fsub(1.0f, 0.0f));
+        class_out[o] = fadd(0.0f, __fdiv_rn(num, den));
+    } else {
+        float m = -INFINITY;
+        for (int k = 0; k < K; ++k) if (k != class_id) m = fmaxf(m, v[k]);
+        class_out[o] = v[class_id];
+        max_out[o] = m;
+    }
+}
+
+// ================================================================================================
+// global min-max normalisation (load_SR_data) and threshold_image
+// ================================================================================================
+__global__ void k_minmax_reduce(const float* __restrict__ p, size_t n, unsigned* __restrict__ mm, size_t per_image) {
+    // blockIdx.y selects the image when per_image != 0 (threshold: one max per image)
+    const int b = blockIdx.y;
+    const float* q = p + (size_t)b * per_image;
+    const size_t cnt = per_image ? per_image : n;
+    float lo = INFINITY, hi = -INFINITY;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < cnt; i += (size_t)gridDim.x * blockDim.x) {
+        const float v = q[i];
+        lo = fminf(lo, v); hi = fmaxf(hi, v);
+    }
+    lo = warp_min(lo); hi = warp_max(hi);
+    if ((threadIdx.x & 31) == 0) { atomicMin(mm + 2 * b, enc(lo)); atomicMax(mm + 2 * b + 1, enc(hi)); }
+}
+
+__global__ void k_minmax_apply(const float* __restrict__ in, size_t n, const unsigned* __restrict__ mm, float new_min,
+                               float new_max, float* __restrict__ out) {
+    const float mn = dec(mm[0]), mx = dec(mm[1]);
+    const float den = (fsub(mx, mn) != 0.0f) ? fsub(mx, mn) : 1.0f;
+    const float scale = fsub(new_max, new_min);
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        out[i] = fadd(new_min, __fdiv_rn(fmul(fsub(in[i], mn), scale), den));
+}
+
+__global__ void k_threshold(const float* __restrict__ x, size_t per_image, const unsigned* __restrict__ mm, float th_factor,
+                            const float* __restrict__ th_mask, int th_value, int* __restrict__ out) {
+    const int b = blockIdx.y;
+    const size_t o = (size_t)b * per_image;
+    if (th_mask) {
+        for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < per_image; i += (size_t)gridDim.x * blockDim.x)
+            out[o + i] = (x[o + i] >= th_mask[o + i]) ? th_value : 0;
+    } else {
+        const float th = fmul(dec(mm[2 * b + 1]), th_factor);
+        for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < per_image; i += (size_t)gridDim.x * blockDim.x)
+            out[o + i] = (x[o + i] > th) ? th_value : 0;
+    }
+}
+
+// ================================================================================================
+// K5: max / mean back-projection.  out = reduce_k rotate(translate(resize(y_k), -shift_k), -angle_k)
+// ================================================================================================
+struct BackXf { float r0, r1, r2, r3, r4, r5, tx, ty; };   // rotate by -angle; translate offsets (+dx,+dy)
+
+__device__ __forceinline__ float upsampled_at(const float* __restrict__ y, int h, int w, int H, int W, int my, int mx,
+                                              float ys, float xs) {
+    // value of tf.image.resize(y,(H,W)) at integer (my,mx); zero outside the canvas (fill of the translate op)
+    if (my < 0 || my >= H || mx < 0 || mx >= W) return 0.0f;
+    const float in_y = fsub(fmul(fadd((float)my, 0.5f), ys), 0.5f), in_x = fsub(fmul(fadd((float)mx, 0.5f), xs), 0.5f);
+    const float fy = floorf(in_y), fx = floorf(in_x);
+    const int y0 = max((int)fy, 0), y1 = min((int)ceilf(in_y), h - 1), x0 = max((int)fx, 0), x1 = min((int)ceilf(in_x), w - 1);
+    const float yl = fsub(in_y, fy), xl = fsub(in_x, fx);
+    const float tl = __ldg(y + y0 * w + x0), tr = __ldg(y + y0 * w + x1), bl = __ldg(y + y1 * w + x0), br = __ldg(y + y1 * w + x1);
+    const float t = fadd(tl, fmul(fsub(tr, tl), xl)), b = fadd(bl, fmul(fsub(br, bl), xl));
+    return fadd(t, fmul(fsub(b, t), yl));
+}
+
+__device__ __forceinline__ float translated_at(const float* __restrict__ y, int h, int w, int H, int W, int qy, int qx,
+                                               float tx, float ty, float ys, float xs) {
+    // value of tfa.image.translate(up, -shift) at integer (qy,qx); zero outside the canvas (fill of the rotate op)
+    if (qy < 0 || qy >= H || qx < 0 || qx >= W) return 0.0f;
+    const float ix = fadd((float)qx, tx), iy = fadd((float)qy, ty);
+    const float fx = floorf(ix), fy = floorf(iy);
+    const float wx0 = fsub(fadd(fx, 1.0f), ix), wx1 = fsub(ix, fx), wy0 = fsub(fadd(fy, 1.0f), iy), wy1 = fsub(iy, fy);
+    const int x0 = (int)fx, y0 = (int)fy;
+    return bilerp(upsampled_at(y, h, w, H, W, y0, x0, ys, xs), upsampled_at(y, h, w, H, W, y0, x0 + 1, ys, xs),
+                  upsampled_at(y, h, w, H, W, y0 + 1, x0, ys, xs), upsampled_at(y, h, w, H, W, y0 + 1, x0 + 1, ys, xs),
+                  wx0, wx1, wy0, wy1);
+}
+
+__global__ void __launch_bounds__(256)
+k_backproject(const float* __restrict__ copies, const BackXf* __restrict__ xf, float* __restrict__ out, int mode, int N, int h,
+              int w, int H, int W) {
+    const int b = blockIdx.z;
+    const int X = blockIdx.x * 32 + (threadIdx.x & 31), Y = blockIdx.y * 8 + (threadIdx.x >> 5);
+    if (X >= W || Y >= H) return;
+    const float ys = (float)h / (float)H, xs = (float)w / (float)W;
+    const float Xf = (float)X, Yf = (float)Y;
+    float accv = 0.0f;
+    for (int k = 0; k < N; ++k) {
+        const BackXf T = xf[(size_t)b * N + k];
+        const float* y = copies + ((size_t)b * N + k) * h * w;
+        const float ix = affine_coord(T.r0, Xf, T.r1, Yf, T.r2), iy = affine_coord(T.r3, Xf, T.r4, Yf, T.r5);
+        const float fx = floorf(ix), fy = floorf(iy);
+        const float wx0 = fsub(fadd(fx, 1.0f), ix), wx1 = fsub(ix, fx), wy0 = fsub(fadd(fy, 1.0f), iy), wy1 = fsub(iy, fy);
+        const int x0 = (int)fx, y0 = (int)fy;
+        const float v = bilerp(translated_at(y, h, w, H, W, y0, x0, T.tx, T.ty, ys, xs),
+                               translated_at(y, h, w, H, W, y0, x0 + 1, T.tx, T.ty, ys, xs),
+                               translated_at(y, h, w, H, W, y0 + 1, x0, T.tx, T.ty, ys, xs),
+                               translated_at(y, h, w, H, W, y0 + 1, x0 + 1, T.tx, T.ty, ys, xs), wx0, wx1, wy0, wy1);
+        if (mode == ASR_BACKPROJECT_MAX) accv = (k == 0) ? v : fmaxf(accv, v);
+        else accv = fadd(accv, v);
+    }
+    if (mode == ASR_BACKPROJECT_MEAN) accv = __fdiv_rn(accv, (float)N);
+    out[((size_t)b * H + Y) * W + X] = accv;
+}
+
+}  // namespace asr
+
+using namespace asr;
+
+extern "C" int asr_warp_affine(const float* d_image, const float* h_angles, const float* h_shifts, int N, int H, int W,
+                               int C, int interp, float* d_out, void* stream) {
+    if (!d_image || !h_angles || !h_shifts || !d_out) return fail(ASR_ENULL, "null argument");
+    if (N <= 0 || H <= 0 || W <= 0 || C <= 0 || C > K3_CMAX) return fail(ASR_EINVAL, "need N,H,W > 0 and 1 <= C <= %d", K3_CMAX);
+    if (N > 65535) return fail(ASR_EINVAL, "N must be <= 65535");
+    if (interp != ASR_INTERP_NEAREST && interp != ASR_INTERP_BILINEAR) return fail(ASR_EINVAL, "unknown interpolation %d", interp);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    std::vector<WarpXf> xf(N);
+    for (int k = 0; k < N; ++k) {
+        float r[8];
+        rotate_matrix(h_angles[k], H, W, r);
+        xf[k] = WarpXf{r[0], r[1], r[2], r[3], r[4], r[5], -h_shifts[2 * k], -h_shifts[2 * k + 1]};
+    }
+    WarpXf* d_xf = nullptr;
+    ASR_CUDA_TRY(cudaMallocAsync((void**)&d_xf, sizeof(WarpXf) * N, st));   // transient table, freed in stream order
+    ASR_CUDA_TRY(cudaMemcpyAsync(d_xf, xf.data(), sizeof(WarpXf) * N, cudaMemcpyHostToDevice, st));
+    const int tiles = ((W + K3_T - 1) / K3_T) * ((H + K3_T - 1) / K3_T);
+    k_warp_affine<<<dim3(tiles, N), K3_THREADS, 0, st>>>(d_image, d_xf, d_out, H, W, C, interp);
+    ASR_CUDA_TRY(cudaGetLastError());
+    ASR_CUDA_TRY(cudaFreeAsync(d_xf, st));
+    return ASR_OK;
+}
+
+extern "C" int asr_opm_extract(const float* d_logits, int N, int h, int w, int K, int class_id, int mode,
+                               float* d_class_out, float* d_max_out, void* d_workspace, void* stream) {
+    if (!d_logits || !d_class_out) return fail(ASR_ENULL, "null argument");
+    if (N <= 0 || h <= 0 || w <= 0 || K <= 0 || K > K4_KMAX) return fail(ASR_EINVAL, "need N,h,w > 0 and 1 <= K <= %d", K4_KMAX);
+    if (class_id < 0 || class_id >= K) return fail(ASR_EINVAL, "class_id %d outside [0,%d)", class_id, K);
+    if (mode < ASR_OPM_ARGMAX || mode > ASR_OPM_SLICE_MAX) return fail(ASR_EINVAL, "unknown OPM mode %d", mode);
+    if (mode == ASR_OPM_SLICE_MAX && !d_max_out) return fail(ASR_ENULL, "slice_max needs d_max_out");
+    if (mode == ASR_OPM_SLICE && !d_workspace) return fail(ASR_ENULL, "slice needs a 2*N float workspace");
+    if (N > 65535) return fail(ASR_EINVAL, "N must be <= 65535");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const size_t px = (size_t)h * w;
+    unsigned* mm = static_cast<unsigned*>(d_workspace);
+    if (mode == ASR_OPM_SLICE) {
+        k_mm_init<<<(N + 127) / 128, 128, 0, st>>>(mm, N);
+        k_copy_minmax<<<dim3(32, N), 256, 0, st>>>(d_logits, px * K, mm);
+    }
+    static bool attr = false;
+    if (!attr) {
+        ASR_CUDA_TRY(cudaFuncSetAttribute(k_opm_extract, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(float) * K4_THREADS * K4_KMAX)));
+        attr = true;
+    }
+    const unsigned blocks = (unsigned)((px + K4_THREADS - 1) / K4_THREADS);
+    k_opm_extract<<<dim3(blocks, N), K4_THREADS, sizeof(float) * K4_THREADS * K, st>>>(d_logits, K, px, class_id, mode, mm,
+                                                                                      d_class_out, d_max_out);
+    ASR_CUDA_TRY(cudaGetLastError());
+    return ASR_OK;
+}
+
+extern "C" int asr_minmax_normalize(const float* d_in, int64_t n, float new_min, float new_max, float* d_out,
+                                    void* d_workspace, void* stream) {
+    if (!d_in || !d_out || !d_workspace) return fail(ASR_ENULL, "null argument");
+    if (n <= 0) return fail(ASR_EINVAL, "n must be positive");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    unsigned* mm = static_cast<unsigned*>(d_workspace);
+    k_mm_init<<<1, 32, 0, st>>>(mm, 1);
+    k_minmax_reduce<<<dim3(296, 1), 256, 0, st>>>(d_in, (size_t)n, mm, 0);
+    k_minmax_apply<<<296 * 2, 256, 0, st>>>(d_in, (size_t)n, mm, new_min, new_max, d_out);
+    ASR_CUDA_TRY(cudaGetLastError());
+    return ASR_OK;
+}
+
+extern "C" int asr_threshold(const float* d_x, int B, int64_t n, int32_t th_value, float th_factor, const float* d_th_mask,
+                             int32_t* d_out, void* d_workspace, void* stream) {
+    if (!d_x || !d_out) return fail(ASR_ENULL, "null argument");
+    if (!d_th_mask && !d_workspace) return fail(ASR_ENULL, "th_factor path needs a 2*B float workspace");
+    if (B <= 0 || n <= 0 || B > 65535) return fail(ASR_EINVAL, "need 0 < B <= 65535 and n > 0");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    unsigned* mm = static_cast<unsigned*>(d_workspace);
+    if (!d_th_mask) {
+        k_mm_init<<<(B + 127) / 128, 128, 0, st>>>(mm, B);
+        k_minmax_reduce<<<dim3(16, B), 256, 0, st>>>(d_x, 0, mm, (size_t)n);
+    }
+    k_threshold<<<dim3(16, B), 256, 0, st>>>(d_x, (size_t)n, mm, th_factor, d_th_mask, th_value, d_out);
+    ASR_CUDA_TRY(cudaGetLastError());
+    return ASR_OK;
+}
+
+extern "C" int asr_backproject_batched(int mode, const float* d_copies, const float* h_angles, const float* h_shifts, int B,
+                                       int N, int h, int w, int H, int W, float* d_out, void* stream) {
+    if (!d_copies || !h_angles || !h_shifts || !d_out) return fail(ASR_ENULL, "null argument");
+    if (mode != ASR_BACKPROJECT_MAX && mode != ASR_BACKPROJECT_MEAN) return fail(ASR_EINVAL, "mode must be max or mean");
+    if (B <= 0 || N <= 0 || h <= 0 || w <= 0 || H <= 0 || W <= 0 || B > 65535) return fail(ASR_EINVAL, "bad shape");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    std::vector<BackXf> xf((size_t)B * N);
+    for (size_t i = 0; i < xf.size(); ++i) {
+        float r[8];
+        rotate_matrix(-h_angles[i], H, W, r);                       // tfa.image.rotate(..., -angles)
+        // tfa.image.translate(..., -shifts): transform offsets -(-dx), -(-dy)
+        xf[i] = BackXf{r[0], r[1], r[2], r[3], r[4], r[5], -(-h_shifts[2 * i]), -(-h_shifts[2 * i + 1])};
+    }
+    BackXf* d_xf = nullptr;
+    ASR_CUDA_TRY(cudaMallocAsync((void**)&d_xf, sizeof(BackXf) * xf.size(), st));
+    ASR_CUDA_TRY(cudaMemcpyAsync(d_xf, xf.data(), sizeof(BackXf) * xf.size(), cudaMemcpyHostToDevice, st));
+    k_backproject<<<dim3((W + 31) / 32, (H + 7) / 8, B), 256, 0, st>>>(d_copies, d_xf, d_out, mode, N, h, w, H, W);
+    ASR_CUDA_TRY(cudaGetLastError());
+    ASR_CUDA_TRY(cudaFreeAsync(d_xf, st));
+    return ASR_OK;
+}

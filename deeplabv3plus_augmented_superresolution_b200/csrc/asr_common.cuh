@@ -1,0 +1,91 @@
+// asr_common.cuh -- shared device/host helpers for libasr (sm_100a only).
+//
+// Numerical contract (DESIGN.md "Exactness"): every kernel on the solve path evaluates the
+// TensorFlow operators in the same fp32 order as the literal op sequence, with NO fused
+// multiply-add, so that results are bit-identical to the un-fused IEEE evaluation.  All arithmetic
+// that feeds a result therefore goes through the explicit round-to-nearest intrinsics below; the
+// library is also compiled with --fmad=false as a second line of defence.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/asr.h"
+
+namespace asr {
+
+// ---- error plumbing ---------------------------------------------------------------------------
+extern thread_local char g_err[512];
+int fail(int code, const char* fmt, ...);
+
+#define ASR_CUDA_TRY(expr)                                                                      \
+    do {                                                                                        \
+        cudaError_t _e = (expr);                                                                \
+        if (_e != cudaSuccess) return ::asr::fail(ASR_ECUDA, "%s: %s", #expr, cudaGetErrorString(_e)); \
+    } while (0)
+
+// ---- exact fp32 building blocks ---------------------------------------------------------------
+__device__ __forceinline__ float fmul(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ float fadd(float a, float b) { return __fadd_rn(a, b); }
+__device__ __forceinline__ float fsub(float a, float b) { return __fadd_rn(a, -b); }
+
+// floor(v) for |v| < 2^22 with two full-rate FADDs and no conversion-pipe instruction:
+// v + 1.5*2^23 rounded toward -inf lands on the integer grid; its low mantissa bits are the integer.
+constexpr float kMagic = 12582912.0f;       // 1.5 * 2^23
+constexpr int kMagicBits = 0x4B400000;      // __float_as_int(kMagic)
+
+struct Floor {
+    float f;   // floorf(v) as float
+    int raw;   // kMagicBits + (int)floorf(v)
+};
+__device__ __forceinline__ Floor floor_magic(float v) {
+    float t = __fadd_rd(v, kMagic);
+    Floor r;
+    r.raw = __float_as_int(t);
+    r.f = __fadd_rn(t, -kMagic);
+    return r;
+}
+
+// ImageProjectiveTransformV3 source coordinate: (t0*x + t1*y) + t2 with separately rounded products.
+__device__ __forceinline__ float affine_coord(float t0, float x, float t1, float y, float t2) {
+    return fadd(fadd(fmul(t0, x), fmul(t1, y)), t2);
+}
+
+// bilinear_interpolation() of the op: (x_ceil-x)*a + (x-x_floor)*b per row, then the same in y.
+__device__ __forceinline__ float bilerp(float v00, float v01, float v10, float v11,
+                                        float wx0, float wx1, float wy0, float wy1) {
+    float top = fadd(fmul(wx0, v00), fmul(wx1, v01));
+    float bot = fadd(fmul(wx0, v10), fmul(wx1, v11));
+    return fadd(fmul(wy0, top), fmul(wy1, bot));
+}
+
+__device__ __forceinline__ float sgn(float v) { return (v > 0.0f) ? 1.0f : ((v < 0.0f) ? -1.0f : 0.0f); }
+
+__device__ __forceinline__ float warp_min(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fminf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// ---- per-copy transforms (host-built, see asr_transforms.cu) ----------------------------------
+// Forward: rotate output->input coefficients t0..t5 and the translate offsets (-dx,-dy).
+struct __align__(16) FwdXf { float r0, r1, r2, r3, r4, r5, tx, ty; };
+// TensorFlow's gradient of the warp op: the same op with the numerically inverted transform.
+struct __align__(16) InvXf { float b0, b1, b2, b3, b4, b5, ux, uy; };
+
+// host side, mirrors tfa.image.angles_to_projective_transforms / translations_to_projective_transforms
+void rotate_matrix(float angle, int H, int W, float t[8]);
+void invert_transform(const float t[8], float tinv[8]);
+
+}  // namespace asr

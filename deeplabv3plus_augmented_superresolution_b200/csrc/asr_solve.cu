@@ -1,0 +1,770 @@
+// asr_solve.cu -- the multi-frame super-resolution inverse solve on B200 (sm_100a).
+//
+// Replaces the TensorFlow op sequence behind Superresolution.augmented_superresolution
+// (superresolution_scripts/superresolution.py:102-137), i.e. per iteration
+//   loss_function (:44-100): tile -> tfa.rotate -> tfa.translate -> tf.image.resize -> sum (D-y)^2, TV, L2, L1
+//   tape.gradient (:126-133): ResizeBilinearGrad -> warp-grad(translate) -> warp-grad(rotate) -> sum over copies
+//   optimizer.apply_gradients (:134-135, optimizer.py:21-41)
+// with two kernels per iteration for a whole batch of images:
+//   k_forward_residual   r_k = D T_k R_k x - y_k              (one CTA per 16x16 LR tile per copy)
+//   k_gradient_update    x' = opt(x, sum_k W_k^grad r_k + reg) (one CTA per 64x64 HR tile, loops copies)
+// Both are gather-form (no atomics) and bit-reproduce the un-fused fp32 evaluation order of the
+// TensorFlow ops (see asr_common.cuh).  DESIGN.md derives the restructurings used here and why
+// each is bit-identical to the literal two-pass evaluation.
+#include <math.h>
+#include <vector>
+
+#include "asr_common.cuh"
+
+namespace asr {
+
+// ================================================================================================
+// device-side per-image parameters
+// ================================================================================================
+struct ImgParams {
+    float two_ldf;      // fl(2 * lambda_df): _SquaredDifferenceGrad scalar
+    float lambda_tv, lambda_l2, lambda_l1;
+    float omb1, omb2;   // fl(1 - beta_1), fl(1 - beta_2)
+    float beta_2;       // adamax
+    float epsilon;
+    float momentum;
+    int optimizer, amsgrad, nesterov;
+    int num_iter;
+    int n_kept;
+    int pad0, pad1;
+};
+// per (iteration, image): x = learning rate of that step, y = optimizer-specific step scale
+// (Adam: lr*sqrt(1-b2^t)/(1-b1^t); Adamax: lr/(1-b1^t))
+typedef float2 Sched;
+
+constexpr int LOG2S = 2;  // HR/LR scale 4 (H == 4h): the 2x2 box of tf.image.resize sits at phases 1,2
+
+// ================================================================================================
+// K0: x0 = tf.image.resize(copies[0], (H,W))  (superresolution.py:112-113)
+// ================================================================================================
+__global__ void k_init_upsample(const float* __restrict__ copies, float* __restrict__ x0, int N, int h, int w, int H,
+                                int W) {
+    const int b = blockIdx.z;
+    const int X = blockIdx.x * blockDim.x + threadIdx.x;
+    const int Y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (X >= W || Y >= H) return;
+    const float* img = copies + (size_t)b * N * h * w;  // copy 0 is the un-augmented one
+    const float ys = (float)h / (float)H, xs = (float)w / (float)W;
+    const float in_y = fsub(fmul(fadd((float)Y, 0.5f), ys), 0.5f);
+    const float in_x = fsub(fmul(fadd((float)X, 0.5f), xs), 0.5f);
+    const float fy = floorf(in_y), fx = floorf(in_x);
+    const int y0 = max((int)fy, 0), y1 = min((int)ceilf(in_y), h - 1);
+    const int x0i = max((int)fx, 0), x1 = min((int)ceilf(in_x), w - 1);
+    const float yl = fsub(in_y, fy), xl = fsub(in_x, fx);
+    const float tl = img[y0 * w + x0i], tr = img[y0 * w + x1], bl = img[y1 * w + x0i], br = img[y1 * w + x1];
+    const float t = fadd(tl, fmul(fsub(tr, tl), xl));
+    const float bb = fadd(bl, fmul(fsub(br, bl), xl));
+    x0[((size_t)b * H + Y) * W + X] = fadd(t, fmul(fsub(bb, t), yl));
+}
+
+// ================================================================================================
+// K1: forward residual
+// ================================================================================================
+// For copy k and LR cell (i,j):  r = resize(translate(rotate(x)))[i,j] - y_k[i,j].
+// The resize reads only z at rows {4i+1,4i+2} x cols {4j+1,4j+2}; each z is a 2x2 stencil of the
+// rotated image p on integer positions, so one cell needs p on a 3x3 patch whose origin is
+// (4j+1+floor(-dx), 4i+1+floor(-dy)).  A CTA stages the x region that patch set can touch in
+// shared memory (zero filled outside the image), evaluates the 48x48 needed p values with the op's
+// exact arithmetic, then a second phase combines them per cell with per-column/row weight tables
+// that carry the literal translate weights, the zero fill of p outside the canvas, and the rare
+// rounding case where floor(fl(Z-dx)) is one above Z+floor(-dx).
+constexpr int K1_T = 16;               // LR tile edge (cells)
+constexpr int K1_THREADS = 192;        // 48 p-columns x 4 row groups
+constexpr int K1_P = 3 * K1_T;         // p positions per tile edge
+constexpr int K1_PBS = K1_P + 1;       // p buffer stride
+constexpr int K1_XS = 96;              // x tile stride (floats), multiple of 32 -> conflict-free gathers
+constexpr int K1_XR = 92;              // x tile rows: 62*sqrt(2)+3 < 92
+constexpr size_t K1_SMEM = sizeof(float) * (K1_XS * K1_XR + K1_P * K1_PBS) + sizeof(float4) * 2 * K1_T;
+
+// translate stencil weights of z-column Z on the window (Z+s, Z+s+1), validity of p folded in
+__device__ __forceinline__ float2 translate_taps(int Z, float t, int s, int limit) {
+    const float iz = fadd((float)Z, t);  // (1*Z + 0*Zy) + t
+    const float f = floorf(iz);
+    const float w0 = fsub(fadd(f, 1.0f), iz), w1 = fsub(iz, f);
+    const int base = Z + s;
+    float wa, wb;
+    if ((int)f == base) { wa = w0; wb = w1; } else { wa = 0.0f; wb = w0; }  // else: floor == base+1, w1 == 0
+    if (base < 0 || base >= limit) wa = 0.0f;
+    if (base + 1 < 0 || base + 1 >= limit) wb = 0.0f;
+    return make_float2(wa, wb);
+}
+
+__global__ void __launch_bounds__(K1_THREADS)
+k_forward_residual(const float* __restrict__ x, const float* __restrict__ copies, float* __restrict__ resid,
+                   const FwdXf* __restrict__ fwd, const int* __restrict__ src_idx,
+                   const ImgParams* __restrict__ ip, int it, int N, int h, int w, int H, int W) {
+    const int b = blockIdx.z, ks = blockIdx.y;
+    const ImgParams P = ip[b];
+    if (ks >= P.n_kept || it >= P.num_iter) return;
+
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float* xt = reinterpret_cast<float*>(smem_raw);          // [K1_XR][K1_XS]
+    float* pb = xt + K1_XS * K1_XR;                          // [K1_P][K1_PBS]
+    float4* colw = reinterpret_cast<float4*>(pb + K1_P * K1_PBS);  // [K1_T] (w1a,w1b,w2a,w2b)
+    float4* roww = colw + K1_T;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int ntj = (w + K1_T - 1) / K1_T;
+    const int j0 = (blockIdx.x % ntj) * K1_T, i0 = (blockIdx.x / ntj) * K1_T;
+    const FwdXf T = fwd[(size_t)b * N + ks];
+    const int sx = (int)floorf(T.tx), sy = (int)floorf(T.ty);
+    const int qx_lo = 4 * j0 + 1 + sx, qy_lo = 4 * i0 + 1 + sy;   // first needed p position
+    constexpr int SPAN = 4 * (K1_T - 1) + 2;                      // last needed = lo + SPAN
+
+    // ---- weight tables (read only after two barriers) ------------------------------------------
+    if (tid < K1_T) {
+        const int Z1 = 4 * (j0 + tid) + 1;
+        const float2 a = translate_taps(Z1, T.tx, sx, W), c = translate_taps(Z1 + 1, T.tx, sx, W);
+        colw[tid] = make_float4(a.x, a.y, c.x, c.y);
+    } else if (tid >= 32 && tid < 32 + K1_T) {
+        const int Z1 = 4 * (i0 + tid - 32) + 1;
+        const float2 a = translate_taps(Z1, T.ty, sy, H), c = translate_taps(Z1 + 1, T.ty, sy, H);
+        roww[tid - 32] = make_float4(a.x, a.y, c.x, c.y);
+    }
+
+    // ---- source bounding box of the p region: extremes are at the corners (each rounded op is
+    //      monotone in qx and in qy), so the literal coordinates of the corners bound all taps ----
+    float cix, ciy;
+    {
+        const float qx = (float)(qx_lo + ((lane & 1) ? SPAN : 0)), qy = (float)(qy_lo + ((lane & 2) ? SPAN : 0));
+        cix = affine_coord(T.r0, qx, T.r1, qy, T.r2);
+        ciy = affine_coord(T.r3, qx, T.r4, qy, T.r5);
+    }
+    const int bx0 = (int)floorf(warp_min(cix)), bx1 = (int)floorf(warp_max(cix)) + 1;
+    const int by0 = (int)floorf(warp_min(ciy)), by1 = (int)floorf(warp_max(ciy)) + 1;
+    const int bx0a = bx0 & ~3;
+    const int ncol4 = ((bx1 - bx0a) >> 2) + 1, nrow = by1 - by0 + 1;
+    if (ncol4 * 4 > K1_XS || nrow > K1_XR) return;  // cannot happen for a rotation (host checks |r0|+|r1|)
+
+    const bool empty = (bx1 < 0 || bx0 >= W || by1 < 0 || by0 >= H);  // rotated image is all zero here
+    if (!empty) {
+        // ---- stage x[by0..by1][bx0a..] with zero fill --------------------------------------------
+        const float* xb = x + (size_t)b * H * W;
+        for (int row = warp; row < nrow; row += K1_THREADS / 32) {
+            const int gy = by0 + row;
+            if (lane < ncol4) {
+                const int gx = bx0a + 4 * lane;
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (gy >= 0 && gy < H && gx >= 0 && gx < W) v = __ldg(reinterpret_cast<const float4*>(xb + (size_t)gy * W + gx));
+                *reinterpret_cast<float4*>(xt + row * K1_XS + 4 * lane) = v;
+            }
+        }
+        __syncthreads();
+
+        // ---- p = rotate-gather of x at the needed integer positions ------------------------------
+        const int pcn = tid % K1_P, g = tid / K1_P;               // p column, row group (12 rows each)
+        const int qx = qx_lo + 4 * (pcn / 3) + (pcn % 3);
+        const float qxf = (float)qx;
+        const float ax = fmul(T.r0, qxf), ay = fmul(T.r3, qxf);
+        const float qyf0 = (float)(qy_lo + 16 * g);
+        const unsigned cst = 0u - (unsigned)(kMagicBits + by0) * K1_XS - (unsigned)(kMagicBits + bx0a);
+#pragma unroll
+        for (int m = 0; m < 12; ++m) {
+            const float qyf = qyf0 + (float)(4 * (m / 3) + (m % 3));   // exact small-integer add
+            const float ix = fadd(fadd(ax, fmul(T.r1, qyf)), T.r2);
+            const float iy = fadd(fadd(ay, fmul(T.r4, qyf)), T.r5);
+            const Floor fx = floor_magic(ix), fy = floor_magic(iy);
+            const float wx0 = fsub(fadd(fx.f, 1.0f), ix), wx1 = fsub(ix, fx.f);
+            const float wy0 = fsub(fadd(fy.f, 1.0f), iy), wy1 = fsub(iy, fy.f);
+            const float* t0 = xt + ((unsigned)fy.raw * K1_XS + (unsigned)fx.raw + cst);   // wraps mod 2^32 to the tile offset
+            pb[(12 * g + m) * K1_PBS + pcn] = bilerp(t0[0], t0[1], t0[K1_XS], t0[K1_XS + 1], wx0, wx1, wy0, wy1);
+        }
+    }
+    __syncthreads();
+
+    // ---- per cell: translate (2x2 z values), resize (literal lerps at 0.5), minus y --------------
+    const int src = src_idx[(size_t)b * N + ks];
+    const float* yk = copies + ((size_t)b * N + src) * h * w;
+    float* rk = resid + ((size_t)b * N + ks) * h * w;
+    for (int cell = tid; cell < K1_T * K1_T; cell += K1_THREADS) {
+        const int ci = cell / K1_T, cj = cell % K1_T;
+        const int i = i0 + ci, j = j0 + cj;
+        if (i >= h || j >= w) continue;
+        float D = 0.0f;
+        if (!empty) {
+            const float4 wc = colw[cj], wr = roww[ci];
+            float Tx[3][2];
+#pragma unroll
+            for (int bb = 0; bb < 3; ++bb) {
+                const float* pr = pb + (3 * ci + bb) * K1_PBS + 3 * cj;
+                const float p0 = pr[0], p1 = pr[1], p2 = pr[2];
+                Tx[bb][0] = fadd(fmul(wc.x, p0), fmul(wc.y, p1));
+                Tx[bb][1] = fadd(fmul(wc.z, p1), fmul(wc.w, p2));
+            }
+            const float tl = fadd(fmul(wr.x, Tx[0][0]), fmul(wr.y, Tx[1][0]));
+            const float tr = fadd(fmul(wr.x, Tx[0][1]), fmul(wr.y, Tx[1][1]));
+            const float bl = fadd(fmul(wr.z, Tx[1][0]), fmul(wr.w, Tx[2][0]));
+            const float br = fadd(fmul(wr.z, Tx[1][1]), fmul(wr.w, Tx[2][1]));
+            const float top = fadd(tl, fmul(fsub(tr, tl), 0.5f));
+            const float bot = fadd(bl, fmul(fsub(br, bl), 0.5f));
+            D = fadd(top, fmul(fsub(bot, top), 0.5f));
+        }
+        rk[i * w + j] = fsub(D, __ldg(yk + i * w + j));
+    }
+}
+
+// ================================================================================================
+// K2: gradient + regularisers + optimizer step
+// ================================================================================================
+// TensorFlow's gradient of the data term for copy k at HR pixel X is
+//     v_k(X) = bilinear(u_k, Rinv_k X),   u_k(q) = bilinear(g_hr, q + d_k),
+//     g_hr = ResizeBilinearGrad(2*lambda_df*r_k) = 0.25*g on the four positions {4i+1,4i+2}x{4j+1,4j+2}.
+// The CTA owns a 64x64 HR tile and loops over the copies.  For each copy it materialises u_k on the
+// bounding box of Rinv_k(tile) in shared memory, one thread per LR cell writing the 4x4 block of q
+// positions that cell feeds (q+floor(d) in [4c,4c+3]); the block's values follow the literal 2-tap
+// sums, which collapse to w_b*g / (w_a*g + w_b*g) / w_a*g / 0 by phase because the other tap reads
+// an exact zero.  Every thread then gathers 8 pixels from that tile with the op's exact arithmetic
+// and adds them to its accumulators in ascending copy order.  Stages for copies k+3 (box), k+2
+// (weight tables), k+1 (u tile) and k (gather) run in one barrier interval.
+constexpr int K2_T = 64;               // HR tile edge
+constexpr int K2_THREADS = 512;        // 16 warps; thread owns pixels (lane + 32c, warp + 16r), c<2, r<4
+constexpr int K2_US = 96;              // u tile stride: 64*sqrt(2)+2+3 < 96, multiple of 32
+constexpr int K2_UR = 96;              // u tile rows
+struct KBox {
+    unsigned cst;   // word offset folding the magic bias, the box origin and the buffer (mod 2^32)
+    int skip;       // box does not touch the LR grid: u == 0
+    int cbx0, cby0; // first LR cell of the box
+    int ncx, ncy;   // cells per box edge
+    int qx_lo, qy_lo;
+    int inv_ncx;    // ceil(65536 / ncx) for the cell index split
+    int pad[3];
+};
+constexpr size_t K2_SMEM = sizeof(float) * 2 * K2_US * K2_UR + sizeof(float2) * 2 * (K2_US + K2_UR) + sizeof(KBox) * 4;
+
+// literal taps of the inverse-translate gather on the window (q+s, q+s+1).  u_k is an image on the
+// HR canvas: the rotate-gradient gather zero-fills q outside [0,limit), so those columns/rows get
+// zero weights (their u must read as 0 even where q+d lands on a non-zero g_hr).
+__device__ __forceinline__ float2 inv_translate_taps(int q, float u, int s, int limit) {
+    if (q < 0 || q >= limit) return make_float2(0.0f, 0.0f);
+    const float iq = fadd((float)q, u);
+    const float f = floorf(iq);
+    const float w0 = fsub(fadd(f, 1.0f), iq), w1 = fsub(iq, f);
+    return ((int)f == q + s) ? make_float2(w0, w1) : make_float2(0.0f, w0);
+}
+
+template <bool WRITE_GRAD>
+__global__ void __launch_bounds__(K2_THREADS, 2)
+k_gradient_update(const float* __restrict__ x_cur, float* __restrict__ x_next, float* __restrict__ s0,
+                  float* __restrict__ s1, float* __restrict__ s2, const float* __restrict__ resid,
+                  const InvXf* __restrict__ inv, const ImgParams* __restrict__ ip, const Sched* __restrict__ sched,
+                  int it, int N, int h, int w, int H, int W, int B) {
+    const int b = blockIdx.y;
+    const ImgParams P = ip[b];
+    if (it >= P.num_iter) return;
+
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float* ut = reinterpret_cast<float*>(smem_raw);                       // [2][K2_UR][K2_US]
+    float2* colw = reinterpret_cast<float2*>(ut + 2 * K2_US * K2_UR);     // [2][K2_US]
+    float2* roww = colw + 2 * K2_US;                                      // [2][K2_UR]
+    KBox* boxes = reinterpret_cast<KBox*>(roww + 2 * K2_UR);              // [4]
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int ntx = (W + K2_T - 1) / K2_T;
+    const int tx0 = (blockIdx.x % ntx) * K2_T, ty0 = (blockIdx.x / ntx) * K2_T;
+    const InvXf* invb = inv + (size_t)b * N;
+    const float* rb = resid + (size_t)b * N * h * w;
+    const int nk = P.n_kept;
+
+    float Xf[2], Yf[4], acc[8];
+#pragma unroll
+    for (int c = 0; c < 2; ++c) Xf[c] = (float)(tx0 + lane + 32 * c);
+#pragma unroll
+    for (int r = 0; r < 4; ++r) Yf[r] = (float)(ty0 + warp + 16 * r);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[e] = 0.0f;
+
+    for (int step = -3; step < nk; ++step) {
+        // ---- stage A: bounding box of copy step+3 (warp 15, lanes 0-3 = tile corners) --------------
+        if (warp == 15 && step + 3 < nk) {
+            const int kk = step + 3;
+            const InvXf T = invb[kk];
+            const float X = (float)(tx0 + ((lane & 1) ? K2_T - 1 : 0)), Y = (float)(ty0 + ((lane & 2) ? K2_T - 1 : 0));
+            const float cix = affine_coord(T.b0, X, T.b1, Y, T.b2), ciy = affine_coord(T.b3, X, T.b4, Y, T.b5);
+            const int qx0 = (int)floorf(warp_min(cix)), qx1 = (int)floorf(warp_max(cix)) + 1;
+            const int qy0 = (int)floorf(warp_min(ciy)), qy1 = (int)floorf(warp_max(ciy)) + 1;
+            if (lane == 0) {
+                const int sx = (int)floorf(T.ux), sy = (int)floorf(T.uy);
+                KBox bx;
+                bx.cbx0 = (qx0 + sx) >> LOG2S;
+                bx.cby0 = (qy0 + sy) >> LOG2S;
+                const int cbx1 = (qx1 + sx) >> LOG2S, cby1 = (qy1 + sy) >> LOG2S;
+                bx.ncx = cbx1 - bx.cbx0 + 1;
+                bx.ncy = cby1 - bx.cby0 + 1;
+                bx.qx_lo = 4 * bx.cbx0 - sx;
+                bx.qy_lo = 4 * bx.cby0 - sy;
+                bx.skip = (cbx1 < 0 || bx.cbx0 >= w || cby1 < 0 || bx.cby0 >= h || 4 * bx.ncx > K2_US || 4 * bx.ncy > K2_UR);
+                bx.cst = (unsigned)((kk & 1) * (K2_US * K2_UR)) - (unsigned)(kMagicBits + bx.qy_lo) * K2_US -
+                         (unsigned)(kMagicBits + bx.qx_lo);
+                bx.inv_ncx = (65536 + bx.ncx - 1) / bx.ncx;
+                boxes[kk & 3] = bx;
+            }
+        }
+        // ---- stage B: literal translate weights of copy step+2 for every q column / row of its box --
+        if (step + 2 >= 0 && step + 2 < nk && tid < K2_US + K2_UR) {
+            const int kk = step + 2;
+            const KBox bx = boxes[kk & 3];
+            if (!bx.skip) {
+                const InvXf T = invb[kk];
+                if (tid < K2_US) colw[(kk & 1) * K2_US + tid] = inv_translate_taps(bx.qx_lo + tid, T.ux, (int)floorf(T.ux), W);
+                else roww[(kk & 1) * K2_UR + tid - K2_US] = inv_translate_taps(bx.qy_lo + tid - K2_US, T.uy, (int)floorf(T.uy), H);
+            }
+        }
+        // ---- stage C: u tile of copy step+1, one thread per LR cell -> 4x4 block ---------------------
+        if (step + 1 >= 0 && step + 1 < nk) {
+            const int kk = step + 1;
+            const KBox bx = boxes[kk & 3];
+            if (!bx.skip) {
+                float* u = ut + (kk & 1) * (K2_US * K2_UR);
+                const float4* cw4 = reinterpret_cast<const float4*>(colw + (kk & 1) * K2_US);
+                const float4* rw4 = reinterpret_cast<const float4*>(roww + (kk & 1) * K2_UR);
+                const float* rk = rb + (size_t)kk * h * w;
+                const int ncell = bx.ncx * bx.ncy;
+                for (int c = tid; c < ncell; c += K2_THREADS) {
+                    const int cyi = (c * bx.inv_ncx) >> 16, cxi = c - cyi * bx.ncx;
+                    const int cy = bx.cby0 + cyi, cx = bx.cbx0 + cxi;
+                    float r = 0.0f;
+                    if (cy >= 0 && cy < h && cx >= 0 && cx < w) r = __ldg(rk + cy * w + cx);
+                    const float g = fmul(0.25f, fmul(P.two_ldf, r));          // g_hr on the cell's 2x2 positions
+                    const float4 ca = cw4[2 * cxi], cb = cw4[2 * cxi + 1];     // (wa0,wb0,wa1,wb1) (wa2,wb2,wa3,wb3)
+                    const float t0 = fmul(ca.y, g);                           // phase 0: taps (0, g)
+                    const float t1 = fadd(fmul(ca.z, g), fmul(ca.w, g));      // phase 1: taps (g, g)
+                    const float t2 = fmul(cb.x, g);                           // phase 2: taps (g, 0); phase 3: (0, 0)
+                    const float4 ra = rw4[2 * cyi], rc = rw4[2 * cyi + 1];
+                    float4* dst = reinterpret_cast<float4*>(u + (4 * cyi) * K2_US + 4 * cxi);
+                    dst[0] = make_float4(fmul(ra.y, t0), fmul(ra.y, t1), fmul(ra.y, t2), 0.0f);
+                    dst[K2_US / 4] = make_float4(fadd(fmul(ra.z, t0), fmul(ra.w, t0)), fadd(fmul(ra.z, t1), fmul(ra.w, t1)),
+                                                 fadd(fmul(ra.z, t2), fmul(ra.w, t2)), 0.0f);
+                    dst[2 * (K2_US / 4)] = make_float4(fmul(rc.x, t0), fmul(rc.x, t1), fmul(rc.x, t2), 0.0f);
+                    dst[3 * (K2_US / 4)] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+                }
+            }
+        }
+        // ---- stage D: gather copy `step` into the accumulators (ascending copy order) -----------------
+        if (step >= 0) {
+            const KBox bx = boxes[step & 3];
+            if (!bx.skip) {
+                const InvXf T = invb[step];
+                float ax[2], ay[2], bxr[4], byr[4];
+#pragma unroll
+                for (int c = 0; c < 2; ++c) { ax[c] = fmul(T.b0, Xf[c]); ay[c] = fmul(T.b3, Xf[c]); }
+#pragma unroll
+                for (int r = 0; r < 4; ++r) { bxr[r] = fmul(T.b1, Yf[r]); byr[r] = fmul(T.b4, Yf[r]); }
+#pragma unroll
+                for (int r = 0; r < 4; ++r) {
+#pragma unroll
+                    for (int c = 0; c < 2; ++c) {
+                        const float ix = fadd(fadd(ax[c], bxr[r]), T.b2);
+                        const float iy = fadd(fadd(ay[c], byr[r]), T.b5);
+                        const Floor fx = floor_magic(ix), fy = floor_magic(iy);
+                        const float wx0 = fsub(fadd(fx.f, 1.0f), ix), wx1 = fsub(ix, fx.f);
+                        const float wy0 = fsub(fadd(fy.f, 1.0f), iy), wy1 = fsub(iy, fy.f);
+                        const float* t0 = ut + ((unsigned)fy.raw * K2_US + (unsigned)fx.raw + bx.cst);
+                        acc[2 * r + c] = fadd(acc[2 * r + c], bilerp(t0[0], t0[1], t0[K2_US], t0[K2_US + 1], wx0, wx1, wy0, wy1));
+                    }
+                }
+            }
+        }
+        __syncthreads();
+    }
+
+    // ---- epilogue: TV (tf.image.image_gradients), L2, L1, optimizer ---------------
+    const size_t plane = (size_t)H * W;
+    const float* xc = x_cur + (size_t)b * plane;
+    const Sched sc = sched[(size_t)it * B + b];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+            const int X = tx0 + lane + 32 * c, Y = ty0 + warp + 16 * r;
+            if (X >= W || Y >= H) continue;
+            const size_t i = (size_t)Y * W + X;
+            const float xi = xc[i];
+            float g = acc[2 * r + c];
+            if (Y > 0) g = fadd(g, fmul(P.lambda_tv, sgn(fsub(xi, xc[i - W]))));
+            if (X > 0) g = fadd(g, fmul(P.lambda_tv, sgn(fsub(xi, xc[i - 1]))));
+            if (Y < H - 1) g = fsub(g, fmul(P.lambda_tv, sgn(fsub(xc[i + W], xi))));
+            if (X < W - 1) g = fsub(g, fmul(P.lambda_tv, sgn(fsub(xc[i + 1], xi))));
+            g = fadd(g, fmul(P.lambda_l2, fmul(xi, 2.0f)));
+            if (P.lambda_l1 > 0.0f) g = fadd(g, fmul(P.lambda_l1, sgn(xi)));
+            const size_t gi = (size_t)b * plane + i;
+            if (WRITE_GRAD) { x_next[gi] = g; continue; }
+            float xn;
+            switch (P.optimizer) {
+            case ASR_OPT_SGD:
+                if (P.momentum == 0.0f) {
+                    xn = fsub(xi, fmul(sc.x, g));
+                } else {
+                    const float a = fsub(fmul(s0[gi], P.momentum), fmul(sc.x, g));
+                    s0[gi] = a;
+                    xn = P.nesterov ? fadd(xi, fsub(fmul(a, P.momentum), fmul(sc.x, g))) : fadd(xi, a);
+                }
+                break;
+            case ASR_OPT_ADAGRAD: {
+                const float a = fadd(s0[gi], fmul(g, g));
+                s0[gi] = a;
+                xn = fsub(xi, __fdiv_rn(fmul(g, sc.x), fadd(__fsqrt_rn(a), P.epsilon)));
+            } break;
+            case ASR_OPT_ADADELTA: {
+                const float rho = 0.95f, eps = 1e-7f, omr = fsub(1.0f, rho);
+                const float a = fadd(fmul(s0[gi], rho), fmul(fmul(g, g), omr));
+                s0[gi] = a;
+                const float au = s1[gi];
+                const float upd = fmul(fmul(__fsqrt_rn(fadd(au, eps)), __fdiv_rn(1.0f, __fsqrt_rn(fadd(a, eps)))), g);
+                xn = fsub(xi, fmul(upd, sc.x));
+                s1[gi] = fadd(fmul(au, rho), fmul(fmul(upd, upd), omr));
+            } break;
+            case ASR_OPT_ADAMAX: {
+                const float m = fadd(s0[gi], fmul(fsub(g, s0[gi]), P.omb1));
+                s0[gi] = m;
+                const float v = fmaxf(fmul(P.beta_2, s1[gi]), fabsf(g));
+                s1[gi] = v;
+                xn = fsub(xi, fmul(sc.y, __fdiv_rn(m, fadd(v, P.epsilon))));
+            } break;
+            default: {
+                const float m = fadd(s0[gi], fmul(fsub(g, s0[gi]), P.omb1));
+                const float v = fadd(s1[gi], fmul(fsub(fmul(g, g), s1[gi]), P.omb2));
+                s0[gi] = m;
+                s1[gi] = v;
+                float den = v;
+                if (P.amsgrad) { den = fmaxf(s2[gi], v); s2[gi] = den; }
+                xn = fsub(xi, __fdiv_rn(fmul(m, sc.y), fadd(__fsqrt_rn(den), P.epsilon)));
+            } break;
+            }
+            x_next[gi] = xn;
+        }
+    }
+}
+
+// ================================================================================================
+// loss of one evaluation (superresolution.py:71-98), double accumulators
+// ================================================================================================
+__global__ void k_loss_terms(const float* __restrict__ xa, const float* __restrict__ xb_, const float* __restrict__ resid,
+                             const ImgParams* __restrict__ ip, double* __restrict__ accum, int N, int h, int w, int H, int W) {
+    const int b = blockIdx.y;
+    const ImgParams P = ip[b];
+    // x of the last evaluation lives in buffer (num_iter-1)&1
+    const float* x = (((P.num_iter - 1) & 1) ? xb_ : xa) + (size_t)b * H * W;
+    const float* r = resid + (size_t)b * N * h * w;
+    const size_t nr = (size_t)P.n_kept * h * w, nx = (size_t)H * W;
+    double df = 0.0, tv = 0.0, l2 = 0.0, l1 = 0.0;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nr; i += (size_t)gridDim.x * blockDim.x) {
+        const double v = r[i];
+        df += v * v;
+    }
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nx; i += (size_t)gridDim.x * blockDim.x) {
+        const int Y = (int)(i / W), X = (int)(i % W);
+        const float xi = x[i];
+        if (Y < H - 1) tv += fabs((double)fsub(x[i + W], xi));
+        if (X < W - 1) tv += fabs((double)fsub(x[i + 1], xi));
+        l2 += (double)xi * (double)xi;
+        l1 += fabs((double)xi);
+    }
+    df = warp_sum(df); tv = warp_sum(tv); l2 = warp_sum(l2); l1 = warp_sum(l1);
+    if ((threadIdx.x & 31) == 0) {
+        atomicAdd(accum + 4 * b + 0, df);
+        atomicAdd(accum + 4 * b + 1, tv);
+        atomicAdd(accum + 4 * b + 2, l2);
+        atomicAdd(accum + 4 * b + 3, l1);
+    }
+}
+
+__global__ void k_loss_final(const double* __restrict__ accum, const AsrSolveParams* __restrict__ hp,
+                             float* __restrict__ loss, int B) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    const AsrSolveParams p = hp[b];
+    float l = fadd(fmul(p.lambda_df, (float)accum[4 * b]), fmul(p.lambda_tv, (float)accum[4 * b + 1]));
+    l = fadd(l, fmul(p.lambda_l2, (float)accum[4 * b + 2]));
+    if (p.lambda_l1 > 0.0f) l = fadd(l, fmul(p.lambda_l1, (float)accum[4 * b + 3]));
+    loss[b] = l;
+}
+
+__global__ void k_select_output(const float* __restrict__ xa, const float* __restrict__ xb_, const ImgParams* __restrict__ ip,
+                                float* __restrict__ out, size_t plane) {
+    const int b = blockIdx.y;
+    const float4* src = reinterpret_cast<const float4*>(((ip[b].num_iter & 1) ? xb_ : xa) + (size_t)b * plane);
+    float4* dst = reinterpret_cast<float4*>(out + (size_t)b * plane);
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < plane / 4; i += (size_t)gridDim.x * blockDim.x) dst[i] = src[i];
+}
+
+__global__ void k_fill(float* __restrict__ p, float v, size_t n) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) p[i] = v;
+}
+
+// ================================================================================================
+// host orchestration
+// ================================================================================================
+static size_t align_up(size_t v, size_t a = 256) { return (v + a - 1) / a * a; }
+
+struct Layout {
+    size_t xa, xb, s0, s1, s2, resid, fwd, inv, src, ip, hp, sched, accum, total;
+};
+
+static Layout make_layout(int B, int N, int h, int w, int H, int W, int max_iter) {
+    Layout L;
+    const size_t plane = sizeof(float) * (size_t)B * H * W;
+    size_t o = 0;
+    L.xa = o; o += align_up(plane);
+    L.xb = o; o += align_up(plane);
+    L.s0 = o; o += align_up(plane);
+    L.s1 = o; o += align_up(plane);
+    L.s2 = o; o += align_up(plane);
+    L.resid = o; o += align_up(sizeof(float) * (size_t)B * N * h * w);
+    L.fwd = o; o += align_up(sizeof(FwdXf) * (size_t)B * N);
+    L.inv = o; o += align_up(sizeof(InvXf) * (size_t)B * N);
+    L.src = o; o += align_up(sizeof(int) * (size_t)B * N);
+    L.ip = o; o += align_up(sizeof(ImgParams) * (size_t)B);
+    L.hp = o; o += align_up(sizeof(AsrSolveParams) * (size_t)B);
+    L.sched = o; o += align_up(sizeof(Sched) * (size_t)B * (size_t)(max_iter > 0 ? max_iter : 1));
+    L.accum = o; o += align_up(sizeof(double) * 4 * (size_t)B);
+    L.total = o;
+    return L;
+}
+
+static int check_shapes(int B, int N, int h, int w, int H, int W) {
+    if (B <= 0 || N <= 0 || h <= 0 || w <= 0) return fail(ASR_EINVAL, "B, N, h, w must be positive (got %d %d %d %d)", B, N, h, w);
+    if (H != 4 * h || W != 4 * w)
+        return fail(ASR_EUNSUPPORTED, "only output_size == 4 * feature_size is implemented (got %dx%d -> %dx%d)", h, w, H, W);
+    if (B > 65535 || N > 65535) return fail(ASR_EINVAL, "B and N must be <= 65535");
+    if (H > (1 << 20) || W > (1 << 20)) return fail(ASR_EINVAL, "image too large for the fp32 floor trick");
+    return ASR_OK;
+}
+
+static int check_params(const AsrSolveParams* p, int n) {
+    for (int i = 0; i < n; ++i) {
+        if (p[i].use_btv) return fail(ASR_EUNSUPPORTED, "use_BTV (bilateral TV, superresolution.py:8-23) is not implemented");
+        if (p[i].optimizer < ASR_OPT_ADAM || p[i].optimizer > ASR_OPT_ADAMAX) return fail(ASR_EINVAL, "unknown optimizer %d", p[i].optimizer);
+        if (p[i].num_iter < 0) return fail(ASR_EINVAL, "num_iter < 0");
+    }
+    return ASR_OK;
+}
+
+// ExponentialDecay (optimizer.py:43-52): lr0 * rate^(i/steps), fp32, non-staircase
+static float lr_at(const AsrSolveParams& p, int i) {
+    if (!p.lr_scheduler) return p.learning_rate;
+    const float e = (float)i / p.decay_steps;
+    return p.learning_rate * powf(p.decay_rate, e);
+}
+
+struct HostTables {
+    std::vector<FwdXf> fwd;
+    std::vector<InvXf> inv;
+    std::vector<int> src;
+    std::vector<ImgParams> ip;
+    std::vector<AsrSolveParams> hp;
+    std::vector<Sched> sched;
+    int max_iter = 0, max_kept = 0;
+};
+
+static void build_tables(const AsrSolveParams* params, int n_params, const float* angles, const float* shifts,
+                         const uint8_t* keep, int B, int N, int H, int W, HostTables& T) {
+    T.fwd.assign((size_t)B * N, FwdXf{});
+    T.inv.assign((size_t)B * N, InvXf{});
+    T.src.assign((size_t)B * N, 0);
+    T.ip.resize(B);
+    T.hp.resize(B);
+    for (int b = 0; b < B; ++b) {
+        const AsrSolveParams& p = params[n_params == 1 ? 0 : b];
+        T.hp[b] = p;
+        int kept = 0;
+        for (int k = 0; k < N; ++k) {
+            if (keep && !keep[(size_t)b * N + k]) continue;
+            float rot[8], roti[8], tr[8], tri[8];
+            rotate_matrix(angles[(size_t)b * N + k], H, W, rot);
+            invert_transform(rot, roti);
+            tr[0] = 1.0f; tr[1] = 0.0f; tr[2] = -shifts[2 * ((size_t)b * N + k)];
+            tr[3] = 0.0f; tr[4] = 1.0f; tr[5] = -shifts[2 * ((size_t)b * N + k) + 1];
+            tr[6] = 0.0f; tr[7] = 0.0f;
+            invert_transform(tr, tri);
+            const size_t o = (size_t)b * N + kept;
+            T.fwd[o] = FwdXf{rot[0], rot[1], rot[2], rot[3], rot[4], rot[5], tr[2], tr[5]};
+            T.inv[o] = InvXf{roti[0], roti[1], roti[2], roti[3], roti[4], roti[5], tri[2], tri[5]};
+            T.src[o] = k;
+            ++kept;
+        }
+        ImgParams q{};
+        q.two_ldf = 2.0f * p.lambda_df;
+        q.lambda_tv = p.lambda_tv; q.lambda_l2 = p.lambda_l2; q.lambda_l1 = p.lambda_l1;
+        q.omb1 = 1.0f - p.beta_1; q.omb2 = 1.0f - p.beta_2; q.beta_2 = p.beta_2;
+        q.epsilon = p.epsilon; q.momentum = p.momentum;
+        q.optimizer = p.optimizer; q.amsgrad = p.amsgrad; q.nesterov = p.nesterov;
+        q.num_iter = p.num_iter; q.n_kept = kept;
+        T.ip[b] = q;
+        if (p.num_iter > T.max_iter) T.max_iter = p.num_iter;
+        if (kept > T.max_kept) T.max_kept = kept;
+    }
+    T.sched.assign((size_t)B * (T.max_iter > 0 ? T.max_iter : 1), make_float2(0.f, 0.f));
+    for (int b = 0; b < B; ++b) {
+        const AsrSolveParams& p = T.hp[b];
+        for (int i = 0; i < p.num_iter; ++i) {
+            const float lr = lr_at(p, i);
+            const float t = (float)(p.step_offset + (int64_t)i + 1);   // optimizer.iterations + 1
+            float y = 0.0f;
+            if (p.optimizer == ASR_OPT_ADAM) {
+                const float b1p = powf(p.beta_1, t), b2p = powf(p.beta_2, t);
+                y = lr * sqrtf(1.0f - b2p) / (1.0f - b1p);
+            } else if (p.optimizer == ASR_OPT_ADAMAX) {
+                const float b1p = powf(p.beta_1, t);
+                y = lr / (1.0f - b1p);
+            }
+            T.sched[(size_t)i * B + b] = make_float2(lr, y);
+        }
+    }
+}
+
+struct Device {
+    float *xa, *xb, *s0, *s1, *s2, *resid;
+    FwdXf* fwd; InvXf* inv; int* src; ImgParams* ip; AsrSolveParams* hp; Sched* sched; double* accum;
+};
+
+static Device bind(void* ws, const Layout& L) {
+    unsigned char* p = static_cast<unsigned char*>(ws);
+    Device D;
+    D.xa = (float*)(p + L.xa); D.xb = (float*)(p + L.xb);
+    D.s0 = (float*)(p + L.s0); D.s1 = (float*)(p + L.s1); D.s2 = (float*)(p + L.s2);
+    D.resid = (float*)(p + L.resid);
+    D.fwd = (FwdXf*)(p + L.fwd); D.inv = (InvXf*)(p + L.inv); D.src = (int*)(p + L.src);
+    D.ip = (ImgParams*)(p + L.ip); D.hp = (AsrSolveParams*)(p + L.hp); D.sched = (Sched*)(p + L.sched);
+    D.accum = (double*)(p + L.accum);
+    return D;
+}
+
+static int upload(const HostTables& T, const Device& D, cudaStream_t st) {
+    ASR_CUDA_TRY(cudaMemcpyAsync(D.fwd, T.fwd.data(), sizeof(FwdXf) * T.fwd.size(), cudaMemcpyHostToDevice, st));
+    ASR_CUDA_TRY(cudaMemcpyAsync(D.inv, T.inv.data(), sizeof(InvXf) * T.inv.size(), cudaMemcpyHostToDevice, st));
+    ASR_CUDA_TRY(cudaMemcpyAsync(D.src, T.src.data(), sizeof(int) * T.src.size(), cudaMemcpyHostToDevice, st));
+    ASR_CUDA_TRY(cudaMemcpyAsync(D.ip, T.ip.data(), sizeof(ImgParams) * T.ip.size(), cudaMemcpyHostToDevice, st));
+    ASR_CUDA_TRY(cudaMemcpyAsync(D.hp, T.hp.data(), sizeof(AsrSolveParams) * T.hp.size(), cudaMemcpyHostToDevice, st));
+    ASR_CUDA_TRY(cudaMemcpyAsync(D.sched, T.sched.data(), sizeof(Sched) * T.sched.size(), cudaMemcpyHostToDevice, st));
+    return ASR_OK;
+}
+
+static int configure_kernels() {
+    static bool done = false;   // attribute is per-function, idempotent; a benign race at worst repeats it
+    if (done) return ASR_OK;
+    ASR_CUDA_TRY(cudaFuncSetAttribute(k_forward_residual, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K1_SMEM));
+    ASR_CUDA_TRY(cudaFuncSetAttribute(k_gradient_update<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K2_SMEM));
+    ASR_CUDA_TRY(cudaFuncSetAttribute(k_gradient_update<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K2_SMEM));
+    done = true;
+    return ASR_OK;
+}
+
+static int launch_loss(const Device& D, int n_params, float* d_loss, int B, int N, int h, int w, int H, int W, cudaStream_t st) {
+    ASR_CUDA_TRY(cudaMemsetAsync(D.accum, 0, sizeof(double) * 4 * B, st));
+    k_loss_terms<<<dim3(64, B), 256, 0, st>>>(D.xa, D.xb, D.resid, D.ip, D.accum, N, h, w, H, W);
+    k_loss_final<<<(B + 127) / 128, 128, 0, st>>>(D.accum, D.hp, d_loss, B);   // D.hp is expanded to one entry per image
+    (void)n_params;
+    return ASR_OK;
+}
+
+}  // namespace asr
+
+using namespace asr;
+
+extern "C" int asr_solve_workspace_bytes(int B, int N, int h, int w, int H, int W, int max_iter, size_t* bytes) {
+    if (!bytes) return fail(ASR_ENULL, "bytes is NULL");
+    if (int e = check_shapes(B, N, h, w, H, W)) return e;
+    *bytes = make_layout(B, N, h, w, H, W, max_iter).total;
+    return ASR_OK;
+}
+
+extern "C" int asr_solve_batched(const AsrSolveParams* params, int n_params, const float* d_copies,
+                                 const float* h_angles, const float* h_shifts, const uint8_t* h_keep, int B, int N,
+                                 int h, int w, int H, int W, float* d_x_out, float* d_loss_out, void* d_workspace,
+                                 size_t workspace_bytes, void* stream) {
+    if (!params || !d_copies || !h_angles || !h_shifts || !d_x_out || !d_workspace) return fail(ASR_ENULL, "null argument");
+    if (n_params != 1 && n_params != B) return fail(ASR_EINVAL, "n_params must be 1 or B");
+    if (int e = check_shapes(B, N, h, w, H, W)) return e;
+    if (int e = check_params(params, n_params)) return e;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+
+    HostTables T;
+    build_tables(params, n_params, h_angles, h_shifts, h_keep, B, N, H, W, T);
+    const Layout L = make_layout(B, N, h, w, H, W, T.max_iter);
+    if (workspace_bytes < L.total) return fail(ASR_EWORKSPACE, "workspace %zu < required %zu bytes", workspace_bytes, L.total);
+    const Device D = bind(d_workspace, L);
+    if (int e = configure_kernels()) return e;
+    if (int e = upload(T, D, st)) return e;
+
+    const size_t plane = (size_t)H * W;
+    ASR_CUDA_TRY(cudaMemsetAsync(D.s0, 0, L.resid - L.s0, st));   // optimizer slots s0,s1,s2 start at zero
+    for (int b = 0; b < B; ++b)   // Adagrad slots start at initial_accumulator_value (optimizer.py:25-27)
+        if (T.hp[b].optimizer == ASR_OPT_ADAGRAD)
+            k_fill<<<64, 256, 0, st>>>(D.s0 + (size_t)b * plane, T.hp[b].initial_accumulator_value, plane);
+    k_init_upsample<<<dim3((W + 31) / 32, (H + 7) / 8, B), dim3(32, 8), 0, st>>>(d_copies, D.xa, N, h, w, H, W);
+
+    const int t1 = ((w + K1_T - 1) / K1_T) * ((h + K1_T - 1) / K1_T);
+    const int t2 = ((W + K2_T - 1) / K2_T) * ((H + K2_T - 1) / K2_T);
+    int group = params[0].images_in_flight > 0 ? params[0].images_in_flight : B;
+    for (int b0 = 0; b0 < B; b0 += group) {
+        const int nb = (B - b0 < group) ? B - b0 : group;
+        int iters = 0;
+        for (int b = b0; b < b0 + nb; ++b) iters = T.hp[b].num_iter > iters ? T.hp[b].num_iter : iters;
+        const size_t po = (size_t)b0 * plane, ro = (size_t)b0 * N * h * w;
+        for (int it = 0; it < iters; ++it) {
+            float* xc = ((it & 1) ? D.xb : D.xa) + po;
+            float* xn = ((it & 1) ? D.xa : D.xb) + po;
+            k_forward_residual<<<dim3(t1, T.max_kept, nb), K1_THREADS, K1_SMEM, st>>>(
+                xc, d_copies + ro, D.resid + ro, D.fwd + (size_t)b0 * N, D.src + (size_t)b0 * N, D.ip + b0, it, N, h, w, H, W);
+            k_gradient_update<false><<<dim3(t2, nb), K2_THREADS, K2_SMEM, st>>>(
+                xc, xn, D.s0 + po, D.s1 + po, D.s2 + po, D.resid + ro, D.inv + (size_t)b0 * N, D.ip + b0,
+                D.sched + b0, it, N, h, w, H, W, B);
+        }
+    }
+    ASR_CUDA_TRY(cudaGetLastError());
+    if (d_loss_out) {
+        if (int e = launch_loss(D, n_params, d_loss_out, B, N, h, w, H, W, st)) return e;
+    }
+    k_select_output<<<dim3(32, B), 256, 0, st>>>(D.xa, D.xb, D.ip, d_x_out, plane);
+    ASR_CUDA_TRY(cudaGetLastError());
+    return ASR_OK;
+}
+
+extern "C" int asr_loss_grad_batched(const AsrSolveParams* params, int n_params, const float* d_x, const float* d_copies,
+                                     const float* h_angles, const float* h_shifts, const uint8_t* h_keep, int B, int N,
+                                     int h, int w, int H, int W, float* d_resid, float* d_grad, float* d_loss_out,
+                                     void* d_workspace, size_t workspace_bytes, void* stream) {
+    if (!params || !d_x || !d_copies || !h_angles || !h_shifts || !d_workspace) return fail(ASR_ENULL, "null argument");
+    if (n_params != 1 && n_params != B) return fail(ASR_EINVAL, "n_params must be 1 or B");
+    if (int e = check_shapes(B, N, h, w, H, W)) return e;
+    if (int e = check_params(params, n_params)) return e;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+
+    std::vector<AsrSolveParams> one(params, params + n_params);
+    for (auto& p : one) p.num_iter = 1;   // a single evaluation at the supplied x
+    HostTables T;
+    build_tables(one.data(), n_params, h_angles, h_shifts, h_keep, B, N, H, W, T);
+    const Layout L = make_layout(B, N, h, w, H, W, 1);
+    if (workspace_bytes < L.total) return fail(ASR_EWORKSPACE, "workspace %zu < required %zu bytes", workspace_bytes, L.total);
+    const Device D = bind(d_workspace, L);
+    if (int e = configure_kernels()) return e;
+    if (int e = upload(T, D, st)) return e;
+
+    const size_t plane = (size_t)H * W;
+    ASR_CUDA_TRY(cudaMemcpyAsync(D.xa, d_x, sizeof(float) * B * plane, cudaMemcpyDeviceToDevice, st));
+    const int t1 = ((w + K1_T - 1) / K1_T) * ((h + K1_T - 1) / K1_T);
+    const int t2 = ((W + K2_T - 1) / K2_T) * ((H + K2_T - 1) / K2_T);
+    k_forward_residual<<<dim3(t1, T.max_kept, B), K1_THREADS, K1_SMEM, st>>>(D.xa, d_copies, D.resid, D.fwd, D.src, D.ip, 0, N, h, w, H, W);
+    k_gradient_update<true><<<dim3(t2, B), K2_THREADS, K2_SMEM, st>>>(D.xa, D.xb, D.s0, D.s1, D.s2, D.resid, D.inv, D.ip,
+                                                                      D.sched, 0, N, h, w, H, W, B);
+    ASR_CUDA_TRY(cudaGetLastError());
+    if (d_grad) ASR_CUDA_TRY(cudaMemcpyAsync(d_grad, D.xb, sizeof(float) * B * plane, cudaMemcpyDeviceToDevice, st));
+    if (d_resid) {
+        // workspace residuals are indexed by kept slot; scatter back to copy order (dropped copies -> 0)
+        ASR_CUDA_TRY(cudaMemsetAsync(d_resid, 0, sizeof(float) * (size_t)B * N * h * w, st));
+        for (int b = 0; b < B; ++b)
+            for (int s = 0; s < T.ip[b].n_kept; ++s)
+                ASR_CUDA_TRY(cudaMemcpyAsync(d_resid + ((size_t)b * N + T.src[(size_t)b * N + s]) * h * w,
+                                             D.resid + ((size_t)b * N + s) * h * w, sizeof(float) * h * w,
+                                             cudaMemcpyDeviceToDevice, st));
+    }
+    if (d_loss_out) {
+        if (int e = launch_loss(D, n_params, d_loss_out, B, N, h, w, H, W, st)) return e;
+    }
+    return ASR_OK;
+}
