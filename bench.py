@@ -1,0 +1,293 @@
+#!/usr/bin/env python
+"""bench.py -- SR-solved images/s for BASELINE.json configs[1] (SR_single_class.py batch shape).
+
+A step = one pass of the hot path over one batch: `--images` images per GPU (default 500), each with
+100 augmented 128x128 copies solved to 512x512 by 300 Adam+AMSGrad iterations (test_SR.py / SR_single_class.py
+hyper-parameters, shared-optimizer step offsets 300*j), then thresholded (th_factor 0.65, class 8).
+Images shard across ranks with no collective in the solve; the masks are gathered to rank 0 (NCCL).
+
+  value   whole-job images/s with the copies already resident in HBM (CUDA events, max over ranks)
+  e2e     the same through the reference-facing Python API with HOST buffers: pinned H2D of the copies,
+          solve, threshold, D2H of the masks, all inside the timed region
+  roofline  dominant solve kernel, CUDA events on its launching stream, algorithmic bytes of SURVEY 8(d)
+  cpu_baseline  the CPU oracle (a port of the reference's TensorFlow arithmetic) on this box's host cores
+
+`--impl reference` times that CPU port alone (the reference itself is TensorFlow 2.7 code that cannot be
+installed here: DESIGN.md), on a bounded sample of the same workload.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np
+
+METRIC = "SR-solved images/sec (100 copies, 128^2->512^2)"
+UNIT = "images/s"
+ITERS, NUM_AUG, LR_HW, HR_HW = 300, 100, (128, 128), (512, 512)
+# per image-iteration, read the LR-sized stack once + read/write x + read/write m, v, vhat
+BYTES_PER_IMAGE_ITER = 4 * NUM_AUG * LR_HW[0] * LR_HW[1] + 8 * 4 * HR_HW[0] * HR_HW[1]
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=2)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--images", type=int, default=500, help="images per GPU per step (weak scaling)")
+    ap.add_argument("--images-in-flight", type=int, default=0, help="images per kernel-launch group (0 = all)")
+    ap.add_argument("--cpu-seconds", type=float, default=15.0, help="budget of the cpu_baseline sample")
+    ap.add_argument("--ref-iters", type=int, default=6, help="--impl reference: solver iterations per step (sample)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def load_peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))), "measured"
+    except Exception:
+        return {"hbm_gbs": 6650.0}, "fallback"
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# clocks during the timed region (B200_PROFILING.md recipe)
+# ---------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, gpu_index):
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+                                          "-i", str(gpu_index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=10)
+        except Exception:
+            self.proc.kill()
+            out = ""
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in out.strip().splitlines():
+            f = [v.strip() for v in line.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# CPU port of the reference (oracle) on a bounded sample
+# ---------------------------------------------------------------------------------------------------------------
+def oracle_sample(copies_np, ang, sh, iters):
+    from oracle import oracle as O
+    P = O.SolveParams(num_iter=int(iters))
+    t = time.perf_counter()
+    O.augmented_superresolution(copies_np, ang, sh, P, output_size=HR_HW)
+    dt = time.perf_counter() - t
+    return dt, O.num_threads()
+
+
+def cpu_baseline(copies_np, ang, sh, budget_s):
+    dt3, cores = oracle_sample(copies_np, ang, sh, 3)
+    per_iter = dt3 / 3
+    n = int(max(5, min(60, budget_s / per_iter)))
+    dt, cores = oracle_sample(copies_np, ang, sh, n)
+    per_iter = dt / n
+    return {"value": 1.0 / (per_iter * ITERS), "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"1 image x {NUM_AUG} copies x {n} of {ITERS} iterations in {dt:.1f} s, extrapolated linearly in iterations"}
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    from deeplabv3plus_augmented_superresolution_b200.synthetic import make_augmented_copies
+    copies, ang, sh = make_augmented_copies(1, NUM_AUG, LR_HW, HR_HW, 0.15, 80, seed=1234, value=1.0)
+    c = copies[0].numpy()
+    times = []
+    cores = 1
+    for s in range(args.warmup + args.steps):
+        dt, cores = oracle_sample(c, ang[0], sh[0], args.ref_iters)
+        if s >= args.warmup:
+            times.append(dt)
+    per_iter = sum(times) / (len(times) * args.ref_iters)
+    value = 1.0 / (per_iter * ITERS)
+    sample = f"each step = 1 image x {NUM_AUG} copies x {args.ref_iters} of {ITERS} iterations; images/s extrapolated linearly in iterations"
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * sum(times) / len(times), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "impl": "reference",
+            "config": {"workload": "configs[1] SR_single_class batch shape: 100 copies, 128^2->512^2, 300 Adam+AMSGrad iterations",
+                       "note": "CPU port (oracle/asr_oracle.c) of the reference's TensorFlow op sequence on all host cores; the reference "
+                               "itself needs tensorflow==2.7.0 + tensorflow-addons==0.15.0, which cannot be installed here", "sample": sample},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import ctypes as C
+    import torch
+    import torch.distributed as dist
+    from deeplabv3plus_augmented_superresolution_b200 import _lib as A, sharding
+    from deeplabv3plus_augmented_superresolution_b200.synthetic import make_augmented_copies
+    from deeplabv3plus_augmented_superresolution_b200.superresolution_scripts.optimizer import Optimizer
+    from deeplabv3plus_augmented_superresolution_b200.superresolution_scripts.superresolution import Superresolution
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: libasr has no CPU path")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    L = A.lib()
+
+    B = args.images
+    n_total = B * world
+    # synthetic stand-in for the hdf5 augmented-copies files: rank r holds images [r*B, (r+1)*B)
+    copies, ang, sh = make_augmented_copies(B, NUM_AUG, LR_HW, HR_HW, 0.15, 80, seed=1234 + 7 * rank, value=1.0, device=dev)
+
+    def make_solver():
+        opt = Optimizer(optimizer="adam", learning_rate=1e-3, amsgrad=True, lr_scheduler=True, decay_steps=60, decay_rate=0.3)
+        return Superresolution(lambda_df=1.0, lambda_tv=0.3, lambda_L2=0.7, lambda_L1=0.0, num_iter=ITERS, num_aug=NUM_AUG,
+                               optimizer=opt, feature_size=LR_HW, output_size=HR_HW)
+
+    ws_th = torch.empty(2 * B, dtype=torch.float32, device=dev)
+    masks = torch.empty((B, HR_HW[0], HR_HW[1]), dtype=torch.int32, device=dev)
+
+    def hot_path(dev_copies):
+        sr = make_solver()
+        sr.optimizer.iterations = ITERS * B * rank          # one optimizer shared by the whole (sharded) run
+        plist = [sr._solve_params(sr.optimizer.iterations + j * ITERS, images_in_flight=args.images_in_flight) for j in range(B)]
+        x = sr.augmented_superresolution_batched(dev_copies, ang, sh, params_list=plist)
+        A.check(L.asr_threshold(x.data_ptr(), B, HR_HW[0] * HR_HW[1], 8, 0.65, None, masks.data_ptr(), ws_th.data_ptr(),
+                                C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+        return sharding.gather_masks(masks.to(torch.uint8), n_total) if world > 1 else masks
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    # ---- device-resident arm ---------------------------------------------------------------------------
+    for _ in range(args.warmup):
+        hot_path(copies)
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    L.asr_profile_enable(1)
+    launches0 = L.asr_kernel_launches()
+    ms = timed(lambda: hot_path(copies), args.steps)
+    launches = L.asr_kernel_launches() - launches0
+    L.asr_profile_enable(0)
+    kms = (C.c_double * 2)(); kcnt = (C.c_longlong * 2)()
+    A.check(L.asr_profile_read(kms, kcnt))
+    clocks = sampler.stop() if sampler else None
+    value = n_total * args.steps / (ms / 1e3)
+
+    # ---- end-to-end arm: host buffers in, host masks out -----------------------------------------------
+    host_copies = torch.empty(copies.shape, dtype=torch.float32, pin_memory=True)
+    host_copies.copy_(copies)
+    host_masks = torch.empty(masks.shape, dtype=torch.int32, pin_memory=True)
+    stage = torch.empty_like(copies)
+
+    def e2e_step():
+        stage.copy_(host_copies, non_blocking=True)
+        hot_path(stage)
+        host_masks.copy_(masks, non_blocking=True)
+
+    e2e_step()
+    ms_e2e = timed(e2e_step, args.steps)
+    e2e = {"value": n_total * args.steps / (ms_e2e / 1e3), "unit": UNIT,
+           "h2d_bytes_per_step": int(host_copies.numel() * 4 * world), "d2h_bytes_per_step": int(host_masks.numel() * 4 * world)}
+
+    lt = torch.tensor([launches], dtype=torch.int64, device=dev)
+    if world > 1:
+        dist.all_reduce(lt)
+
+    if rank == 0:
+        peaks, peak_kind = load_peaks()
+        dom = 1 if kms[1] >= kms[0] else 0
+        names = ["k_forward_residual", "k_gradient_update"]
+        per_launch_images = B if args.images_in_flight <= 0 else min(B, args.images_in_flight)
+        avg_launch_s = (kms[dom] / max(1, kcnt[dom])) / 1e3
+        # launches of a short tail group carry fewer images: use the true mean images per launch
+        images_per_launch = B * ITERS * args.steps / max(1, kcnt[dom])
+        achieved = images_per_launch * BYTES_PER_IMAGE_ITER / avg_launch_s / 1e9
+        traffic = None
+        try:
+            prof = json.load(open(os.path.join(ROOT, "profiles", "solve_traffic.json")))
+            traffic = prof[names[dom]]["dram_bytes_per_image"] * images_per_launch
+        except Exception:
+            pass
+        iter_s = (kms[0] + kms[1]) / 1e3 / max(1, kcnt[1])
+        roofline = {"bound": "hbm", "kernel": names[dom], "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                    "frac": achieved / peaks["hbm_gbs"], "traffic": traffic, "peak_source": f"{peak_kind} (MEASURED_PEAKS.json hbm_gbs)",
+                    "share_of_step": kms[dom] / ms, "avg_launch_ms": avg_launch_s * 1e3,
+                    "forward_ms_total": kms[0], "update_ms_total": kms[1],
+                    "iteration_pair": {"achieved": images_per_launch * BYTES_PER_IMAGE_ITER / iter_s / 1e9,
+                                       "frac": images_per_launch * BYTES_PER_IMAGE_ITER / iter_s / 1e9 / peaks["hbm_gbs"]},
+                    "note": "the solve is FP32-issue bound, not bandwidth bound: see DESIGN.md 'Roofline' and profiles/"}
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+                "data": "synthetic",
+                "config": {"workload": "configs[1] SR_single_class batch: 500 images x 100 copies per GPU, 128^2->512^2, 300 Adam+AMSGrad "
+                                       "iterations (test_SR.py hyper-parameters, shared-optimizer step offsets), threshold 0.65",
+                           "images_per_gpu": B, "num_aug": NUM_AUG, "iterations": ITERS, "images_in_flight": args.images_in_flight,
+                           "parallelism": f"images sharded over {world} GPU(s), no collective in the solve, NCCL gather of masks",
+                           "l2": f"inputs are {copies.numel() * 4 / 1e9:.2f} GB per GPU (> 126 MB L2), no flush needed",
+                           "parity": "bit-identical to the CPU oracle (tests/test_parity_gpu.py)"},
+                "clocks": clocks, "e2e": e2e, "gpu_launches": int(lt.item()), "roofline": roofline}
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline(copies[0].cpu().numpy(), ang[0], sh[0], args.cpu_seconds)
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -306,7 +306,7 @@ extern "C" int asr_warp_affine(const float* d_image, const float* h_angles, cons
     ASR_CUDA_TRY(cudaMallocAsync((void**)&d_xf, sizeof(WarpXf) * N, st));   // transient table, freed in stream order
     ASR_CUDA_TRY(cudaMemcpyAsync(d_xf, xf.data(), sizeof(WarpXf) * N, cudaMemcpyHostToDevice, st));
     const int tiles = ((W + K3_T - 1) / K3_T) * ((H + K3_T - 1) / K3_T);
-    k_warp_affine<<<dim3(tiles, N), K3_THREADS, 0, st>>>(d_image, d_xf, d_out, H, W, C, interp);
+    ASR_LAUNCH(k_warp_affine, dim3(tiles, N), K3_THREADS, 0, st, d_image, d_xf, d_out, H, W, C, interp);
     ASR_CUDA_TRY(cudaGetLastError());
     ASR_CUDA_TRY(cudaFreeAsync(d_xf, st));
     return ASR_OK;
@@ -325,8 +325,8 @@ extern "C" int asr_opm_extract(const float* d_logits, int N, int h, int w, int K
     const size_t px = (size_t)h * w;
     unsigned* mm = static_cast<unsigned*>(d_workspace);
     if (mode == ASR_OPM_SLICE) {
-        k_mm_init<<<(N + 127) / 128, 128, 0, st>>>(mm, N);
-        k_copy_minmax<<<dim3(32, N), 256, 0, st>>>(d_logits, px * K, mm);
+        ASR_LAUNCH(k_mm_init, (N + 127) / 128, 128, 0, st, mm, N);
+        ASR_LAUNCH(k_copy_minmax, dim3(32, N), 256, 0, st, d_logits, px * K, mm);
     }
     static bool attr = false;
     if (!attr) {
@@ -334,7 +334,7 @@ extern "C" int asr_opm_extract(const float* d_logits, int N, int h, int w, int K
         attr = true;
     }
     const unsigned blocks = (unsigned)((px + K4_THREADS - 1) / K4_THREADS);
-    k_opm_extract<<<dim3(blocks, N), K4_THREADS, sizeof(float) * K4_THREADS * K, st>>>(d_logits, K, px, class_id, mode, mm,
+    ASR_LAUNCH(k_opm_extract, dim3(blocks, N), K4_THREADS, sizeof(float) * K4_THREADS * K, st, d_logits, K, px, class_id, mode, mm,
                                                                                       d_class_out, d_max_out);
     ASR_CUDA_TRY(cudaGetLastError());
     return ASR_OK;
@@ -346,9 +346,9 @@ extern "C" int asr_minmax_normalize(const float* d_in, int64_t n, float new_min,
     if (n <= 0) return fail(ASR_EINVAL, "n must be positive");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     unsigned* mm = static_cast<unsigned*>(d_workspace);
-    k_mm_init<<<1, 32, 0, st>>>(mm, 1);
-    k_minmax_reduce<<<dim3(296, 1), 256, 0, st>>>(d_in, (size_t)n, mm, 0);
-    k_minmax_apply<<<296 * 2, 256, 0, st>>>(d_in, (size_t)n, mm, new_min, new_max, d_out);
+    ASR_LAUNCH(k_mm_init, 1, 32, 0, st, mm, 1);
+    ASR_LAUNCH(k_minmax_reduce, dim3(296, 1), 256, 0, st, d_in, (size_t)n, mm, 0);
+    ASR_LAUNCH(k_minmax_apply, 296 * 2, 256, 0, st, d_in, (size_t)n, mm, new_min, new_max, d_out);
     ASR_CUDA_TRY(cudaGetLastError());
     return ASR_OK;
 }
@@ -361,10 +361,10 @@ extern "C" int asr_threshold(const float* d_x, int B, int64_t n, int32_t th_valu
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     unsigned* mm = static_cast<unsigned*>(d_workspace);
     if (!d_th_mask) {
-        k_mm_init<<<(B + 127) / 128, 128, 0, st>>>(mm, B);
-        k_minmax_reduce<<<dim3(16, B), 256, 0, st>>>(d_x, 0, mm, (size_t)n);
+        ASR_LAUNCH(k_mm_init, (B + 127) / 128, 128, 0, st, mm, B);
+        ASR_LAUNCH(k_minmax_reduce, dim3(16, B), 256, 0, st, d_x, 0, mm, (size_t)n);
     }
-    k_threshold<<<dim3(16, B), 256, 0, st>>>(d_x, (size_t)n, mm, th_factor, d_th_mask, th_value, d_out);
+    ASR_LAUNCH(k_threshold, dim3(16, B), 256, 0, st, d_x, (size_t)n, mm, th_factor, d_th_mask, th_value, d_out);
     ASR_CUDA_TRY(cudaGetLastError());
     return ASR_OK;
 }
@@ -385,7 +385,7 @@ extern "C" int asr_backproject_batched(int mode, const float* d_copies, const fl
     BackXf* d_xf = nullptr;
     ASR_CUDA_TRY(cudaMallocAsync((void**)&d_xf, sizeof(BackXf) * xf.size(), st));
     ASR_CUDA_TRY(cudaMemcpyAsync(d_xf, xf.data(), sizeof(BackXf) * xf.size(), cudaMemcpyHostToDevice, st));
-    k_backproject<<<dim3((W + 31) / 32, (H + 7) / 8, B), 256, 0, st>>>(d_copies, d_xf, d_out, mode, N, h, w, H, W);
+    ASR_LAUNCH(k_backproject, dim3((W + 31) / 32, (H + 7) / 8, B), 256, 0, st, d_copies, d_xf, d_out, mode, N, h, w, H, W);
     ASR_CUDA_TRY(cudaGetLastError());
     ASR_CUDA_TRY(cudaFreeAsync(d_xf, st));
     return ASR_OK;

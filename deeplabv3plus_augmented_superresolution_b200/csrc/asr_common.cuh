@@ -25,6 +25,24 @@ int fail(int code, const char* fmt, ...);
         if (_e != cudaSuccess) return ::asr::fail(ASR_ECUDA, "%s: %s", #expr, cudaGetErrorString(_e)); \
     } while (0)
 
+// ---- launch accounting / optional per-kernel timing (asr_kernel_launches, asr_profile_*) -------
+// Every kernel launch of the library goes through ASR_LAUNCH so that bench.py can report how many of
+// our kernels ran in its timed region; with profiling on, the two solve kernels are bracketed by
+// CUDA events on the launching stream (summed by asr_profile_read after a stream sync).
+void count_launch();
+void profile_mark(int slot, cudaStream_t st, bool begin);   // slot 0 = forward residual, 1 = gradient/update
+#define ASR_LAUNCH(kernel, grid, block, smem, st, ...)          \
+    do {                                                        \
+        ::asr::count_launch();                                  \
+        kernel<<<grid, block, smem, st>>>(__VA_ARGS__);         \
+    } while (0)
+#define ASR_LAUNCH_TIMED(slot, kernel, grid, block, smem, st, ...) \
+    do {                                                           \
+        ::asr::profile_mark(slot, st, true);                       \
+        ASR_LAUNCH(kernel, grid, block, smem, st, __VA_ARGS__);    \
+        ::asr::profile_mark(slot, st, false);                      \
+    } while (0)
+
 // ---- exact fp32 building blocks ---------------------------------------------------------------
 __device__ __forceinline__ float fmul(float a, float b) { return __fmul_rn(a, b); }
 __device__ __forceinline__ float fadd(float a, float b) { return __fadd_rn(a, b); }

@@ -9,6 +9,10 @@
 #include <stdarg.h>
 #include <string.h>
 
+#include <atomic>
+#include <mutex>
+#include <vector>
+
 #include "asr_common.cuh"
 
 namespace asr {
@@ -66,7 +70,64 @@ void invert_transform(const float t[8], float tinv[8]) {
     for (int i = 0; i < 8; ++i) tinv[i] = inv[i] / inv[8];
 }
 
+// ---- launch accounting and optional kernel timing ------------------------------------------------
+static std::atomic<long long> g_launches{0};
+static std::mutex g_prof_mu;
+static bool g_prof_on = false;
+struct ProfSpan { cudaEvent_t a, b; int slot; };
+static std::vector<ProfSpan> g_spans;
+static std::vector<cudaEvent_t> g_pool;
+static cudaEvent_t g_open[2];
+
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+
+static cudaEvent_t take_event() {
+    if (!g_pool.empty()) { cudaEvent_t e = g_pool.back(); g_pool.pop_back(); return e; }
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    return e;
+}
+
+void profile_mark(int slot, cudaStream_t st, bool begin) {
+    if (!g_prof_on) return;
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    if (begin) {
+        g_open[slot] = take_event();
+        cudaEventRecord(g_open[slot], st);
+    } else {
+        cudaEvent_t e = take_event();
+        cudaEventRecord(e, st);
+        g_spans.push_back(ProfSpan{g_open[slot], e, slot});
+    }
+}
+
 }  // namespace asr
+
+extern "C" long long asr_kernel_launches(void) { return asr::g_launches.load(); }
+
+extern "C" int asr_profile_enable(int on) {
+    std::lock_guard<std::mutex> lk(asr::g_prof_mu);
+    asr::g_prof_on = on != 0;
+    return ASR_OK;
+}
+
+extern "C" int asr_profile_read(double* ms, long long* count) {
+    if (!ms || !count) return asr::fail(ASR_ENULL, "null argument");
+    std::lock_guard<std::mutex> lk(asr::g_prof_mu);
+    ms[0] = ms[1] = 0.0;
+    count[0] = count[1] = 0;
+    for (auto& s : asr::g_spans) {
+        ASR_CUDA_TRY(cudaEventSynchronize(s.b));
+        float t = 0.f;
+        ASR_CUDA_TRY(cudaEventElapsedTime(&t, s.a, s.b));
+        ms[s.slot] += t;
+        count[s.slot] += 1;
+        asr::g_pool.push_back(s.a);
+        asr::g_pool.push_back(s.b);
+    }
+    asr::g_spans.clear();
+    return ASR_OK;
+}
 
 extern "C" int asr_version(void) { return ASR_VERSION; }
 extern "C" const char* asr_last_error(void) { return asr::g_err; }

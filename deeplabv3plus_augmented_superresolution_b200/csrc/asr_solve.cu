@@ -656,8 +656,8 @@ static int configure_kernels() {
 
 static int launch_loss(const Device& D, int n_params, float* d_loss, int B, int N, int h, int w, int H, int W, cudaStream_t st) {
     ASR_CUDA_TRY(cudaMemsetAsync(D.accum, 0, sizeof(double) * 4 * B, st));
-    k_loss_terms<<<dim3(64, B), 256, 0, st>>>(D.xa, D.xb, D.resid, D.ip, D.accum, N, h, w, H, W);
-    k_loss_final<<<(B + 127) / 128, 128, 0, st>>>(D.accum, D.hp, d_loss, B);   // D.hp is expanded to one entry per image
+    ASR_LAUNCH(k_loss_terms, dim3(64, B), 256, 0, st, D.xa, D.xb, D.resid, D.ip, D.accum, N, h, w, H, W);
+    ASR_LAUNCH(k_loss_final, (B + 127) / 128, 128, 0, st, D.accum, D.hp, d_loss, B);   // D.hp is expanded to one entry per image
     (void)n_params;
     return ASR_OK;
 }
@@ -695,8 +695,8 @@ extern "C" int asr_solve_batched(const AsrSolveParams* params, int n_params, con
     ASR_CUDA_TRY(cudaMemsetAsync(D.s0, 0, L.resid - L.s0, st));   // optimizer slots s0,s1,s2 start at zero
     for (int b = 0; b < B; ++b)   // Adagrad slots start at initial_accumulator_value (optimizer.py:25-27)
         if (T.hp[b].optimizer == ASR_OPT_ADAGRAD)
-            k_fill<<<64, 256, 0, st>>>(D.s0 + (size_t)b * plane, T.hp[b].initial_accumulator_value, plane);
-    k_init_upsample<<<dim3((W + 31) / 32, (H + 7) / 8, B), dim3(32, 8), 0, st>>>(d_copies, D.xa, N, h, w, H, W);
+            ASR_LAUNCH(k_fill, 64, 256, 0, st, D.s0 + (size_t)b * plane, T.hp[b].initial_accumulator_value, plane);
+    ASR_LAUNCH(k_init_upsample, dim3((W + 31) / 32, (H + 7) / 8, B), dim3(32, 8), 0, st, d_copies, D.xa, N, h, w, H, W);
 
     const int t1 = ((w + K1_T - 1) / K1_T) * ((h + K1_T - 1) / K1_T);
     const int t2 = ((W + K2_T - 1) / K2_T) * ((H + K2_T - 1) / K2_T);
@@ -709,9 +709,9 @@ extern "C" int asr_solve_batched(const AsrSolveParams* params, int n_params, con
         for (int it = 0; it < iters; ++it) {
             float* xc = ((it & 1) ? D.xb : D.xa) + po;
             float* xn = ((it & 1) ? D.xa : D.xb) + po;
-            k_forward_residual<<<dim3(t1, T.max_kept, nb), K1_THREADS, K1_SMEM, st>>>(
+            ASR_LAUNCH_TIMED(0, k_forward_residual, dim3(t1, T.max_kept, nb), K1_THREADS, K1_SMEM, st, 
                 xc, d_copies + ro, D.resid + ro, D.fwd + (size_t)b0 * N, D.src + (size_t)b0 * N, D.ip + b0, it, N, h, w, H, W);
-            k_gradient_update<false><<<dim3(t2, nb), K2_THREADS, K2_SMEM, st>>>(
+            ASR_LAUNCH_TIMED(1, (k_gradient_update<false>), dim3(t2, nb), K2_THREADS, K2_SMEM, st, 
                 xc, xn, D.s0 + po, D.s1 + po, D.s2 + po, D.resid + ro, D.inv + (size_t)b0 * N, D.ip + b0,
                 D.sched + b0, it, N, h, w, H, W, B);
         }
@@ -720,7 +720,7 @@ extern "C" int asr_solve_batched(const AsrSolveParams* params, int n_params, con
     if (d_loss_out) {
         if (int e = launch_loss(D, n_params, d_loss_out, B, N, h, w, H, W, st)) return e;
     }
-    k_select_output<<<dim3(32, B), 256, 0, st>>>(D.xa, D.xb, D.ip, d_x_out, plane);
+    ASR_LAUNCH(k_select_output, dim3(32, B), 256, 0, st, D.xa, D.xb, D.ip, d_x_out, plane);
     ASR_CUDA_TRY(cudaGetLastError());
     return ASR_OK;
 }
@@ -749,8 +749,8 @@ extern "C" int asr_loss_grad_batched(const AsrSolveParams* params, int n_params,
     ASR_CUDA_TRY(cudaMemcpyAsync(D.xa, d_x, sizeof(float) * B * plane, cudaMemcpyDeviceToDevice, st));
     const int t1 = ((w + K1_T - 1) / K1_T) * ((h + K1_T - 1) / K1_T);
     const int t2 = ((W + K2_T - 1) / K2_T) * ((H + K2_T - 1) / K2_T);
-    k_forward_residual<<<dim3(t1, T.max_kept, B), K1_THREADS, K1_SMEM, st>>>(D.xa, d_copies, D.resid, D.fwd, D.src, D.ip, 0, N, h, w, H, W);
-    k_gradient_update<true><<<dim3(t2, B), K2_THREADS, K2_SMEM, st>>>(D.xa, D.xb, D.s0, D.s1, D.s2, D.resid, D.inv, D.ip,
+    ASR_LAUNCH_TIMED(0, k_forward_residual, dim3(t1, T.max_kept, B), K1_THREADS, K1_SMEM, st, D.xa, d_copies, D.resid, D.fwd, D.src, D.ip, 0, N, h, w, H, W);
+    ASR_LAUNCH_TIMED(1, (k_gradient_update<true>), dim3(t2, B), K2_THREADS, K2_SMEM, st, D.xa, D.xb, D.s0, D.s1, D.s2, D.resid, D.inv, D.ip,
                                                                       D.sched, 0, N, h, w, H, W, B);
     ASR_CUDA_TRY(cudaGetLastError());
     if (d_grad) ASR_CUDA_TRY(cudaMemcpyAsync(d_grad, D.xb, sizeof(float) * B * plane, cudaMemcpyDeviceToDevice, st));

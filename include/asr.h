@@ -69,6 +69,14 @@ typedef struct AsrSolveParams {
 int asr_version(void);
 const char* asr_last_error(void);
 
+/* Measurement hooks (bench.py): cumulative number of kernels this library has launched, and optional
+ * CUDA-event timing of the two solve kernels on their launching stream.  asr_profile_read waits for
+ * the recorded events, returns {forward-residual, gradient/update} total milliseconds and launch
+ * counts since the previous read, and clears them. */
+long long asr_kernel_launches(void);
+int asr_profile_enable(int on);
+int asr_profile_read(double* ms2, long long* count2);
+
 /* ---- superresolution.py:102-137  Superresolution.augmented_superresolution ------------------
  * Solves B independent images in one call (SR_single_class.py:83-107 loops over them one by one).
  *   params      h_ array of n_params structs; n_params == 1 (shared) or B (one per image, as the

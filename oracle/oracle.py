@@ -133,7 +133,9 @@ def projective_transform(images, transforms, interpolation="bilinear", fill_valu
 def rotate(images, angles, interpolation="bilinear"):
     images = _c32(images)
     N, H, W, _ = images.shape
-    angles = np.broadcast_to(np.asarray(angles, np.float32).reshape(-1), (N,)) if np.ndim(angles) == 0 or len(np.atleast_1d(angles)) == 1 else np.asarray(angles, np.float32)
+    angles = np.asarray(angles, np.float32).reshape(-1)
+    if angles.shape[0] == 1 and N > 1:
+        angles = np.repeat(angles, N)
     tr = np.stack([rotate_matrix(float(a), H, W) for a in angles])
     return projective_transform(images, tr, interpolation)
 

@@ -1,0 +1,151 @@
+"""CPU tests of the host-side mirror of the reference interface: hdf5 hand-off layout, parameter
+mapping, the shared optimizer step counter, copy-dropout mask, path helpers, sharding + gather."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from deeplabv3plus_augmented_superresolution_b200 import hdf5_lite, sharding, utils
+from deeplabv3plus_augmented_superresolution_b200.superresolution_scripts.optimizer import Optimizer
+from deeplabv3plus_augmented_superresolution_b200.superresolution_scripts.superresolution import Superresolution
+from deeplabv3plus_augmented_superresolution_b200.superresolution_scripts import superres_utils as SU
+
+
+def _write_case(path, n=6, mode="argmax", with_max=False):
+    rng = np.random.RandomState(0)
+    cm = [rng.rand(8, 8, 1).astype(np.float32) for _ in range(n)]
+    f = hdf5_lite.File(path, "w")
+    f.create_dataset("class_masks", data=cm)
+    if with_max:
+        f.create_dataset("max_masks", data=[c * 2 for c in cm])
+    f.create_dataset("angles", data=rng.rand(n).astype(np.float32))
+    f.create_dataset("shifts", data=rng.rand(n, 2).astype(np.float32))
+    f.attrs["filename"] = "2007_000032"
+    f.attrs["mode"] = mode
+    f.attrs["angle_max"] = 0.15
+    f.attrs["shift_max"] = 80
+    f.close()
+    return cm
+
+
+def test_hdf5_layout_roundtrip(tmp_path):
+    p = str(tmp_path / "2007_000032.hdf5")
+    cm = _write_case(p, with_max=True, mode="slice_max")
+    raw = open(p, "rb").read()
+    assert raw[:8] == b"\x89HDF\r\n\x1a\n" and raw[8] == 0                 # superblock v0, as h5py's default
+    assert int.from_bytes(raw[40:48], "little") == len(raw)               # end-of-file address
+    assert raw.count(b"TREE") == 1 and raw.count(b"SNOD") == 1 and raw.count(b"HEAP") == 1 and raw.count(b"GCOL") == 1
+    f = hdf5_lite.File(p, "r")
+    assert sorted(f) == ["angles", "class_masks", "max_masks", "shifts"]
+    assert f["class_masks"].shape == (6, 8, 8, 1) and f["class_masks"].dtype == np.float32
+    assert f["shifts"].shape == (6, 2) and f["angles"].shape == (6,)
+    np.testing.assert_array_equal(f["class_masks"][:4], np.stack(cm)[:4])
+    assert f.attrs["filename"] == "2007_000032" and isinstance(f.attrs["mode"], str) and f.attrs["mode"] == "slice_max"
+    assert f.attrs["angle_max"] == 0.15 and f.attrs["shift_max"] == 80 and isinstance(f.attrs["shift_max"], int)
+    assert SU.check_hdf5_validity(f, num_aug=6) and not SU.check_hdf5_validity(f, num_aug=7)
+    with pytest.raises(KeyError):
+        f["nope"]
+    f.close()
+    with pytest.raises(hdf5_lite.Hdf5FormatError):
+        bad = tmp_path / "bad.hdf5"
+        bad.write_bytes(b"not hdf5 at all" * 10)
+        hdf5_lite.File(str(bad), "r")
+
+
+def test_path_helpers(tmp_path):
+    for name in ("2008_000003", "2007_000129", "2007_000032"):
+        (tmp_path / f"{name}.hdf5").write_bytes(b"")
+    (tmp_path / "notes.txt").write_text("x")
+    got = [os.path.basename(p) for p in SU.list_precomputed_data_paths(str(tmp_path), sort=True)]
+    assert got == ["2007_000032.hdf5", "2007_000129.hdf5", "2008_000003.hdf5"]
+    lst = tmp_path / "list.txt"
+    lst.write_text("2007_000129\n2007_000032\n")
+    assert [os.path.basename(p) for p in SU.get_img_paths(str(lst), "/imgs")] == ["2007_000032.jpg", "2007_000129.jpg"]
+    assert SU.normalize_coefficients({"a": 1.0, "b": 3.0}) == {"a": 0.25, "b": 0.75}
+    x = np.array([[1.0, 3.0]], np.float32)
+    np.testing.assert_array_equal(SU.min_max_normalization(x, 0.0, 1.0), [[0.0, 1.0]])
+    np.testing.assert_array_equal(SU.min_max_normalization(np.full((2, 2), 4.0, np.float32), 0.0, 1.0), np.zeros((2, 2)))
+
+
+def test_optimizer_and_params_mapping():
+    o = Optimizer(optimizer="adam", learning_rate=1e-3, amsgrad=True, lr_scheduler=True, decay_steps=60, decay_rate=0.3)
+    assert o.kind == "adam" and o.iterations == 0
+    assert Optimizer(optimizer="something-else").kind == "adam"        # reference falls through to Adam (optimizer.py:36-41)
+    assert abs(float(o.lr_decay(60)) - 3e-4) < 1e-9
+    s = Superresolution(lambda_df=1.0, lambda_tv=0.3, lambda_L2=0.7, lambda_L1=0.0, num_iter=300, num_aug=100, optimizer=o,
+                        feature_size=(128, 128))
+    p = s._solve_params(step_offset=600)
+    c = p.to_c()
+    assert (c.num_iter, c.optimizer, c.amsgrad, c.lr_scheduler, c.step_offset) == (300, 0, 1, 1, 600)
+    assert abs(c.lambda_tv - 0.3) < 1e-7 and abs(c.decay_rate - 0.3) < 1e-7 and c.decay_steps == 60.0
+    with pytest.raises(Exception, match="must provide an instance of the Optimizer"):
+        Superresolution(1, 1, 1, 0)._check_optimizer()
+    with pytest.raises(NotImplementedError):
+        Superresolution(1, 1, 1, 0, optimizer=o, output_size=(512, 512))._check_sizes(64, 64)   # the (64,64) default
+
+
+def test_copy_dropout_mask_is_frozen_like_a_traced_function():
+    o = Optimizer()
+    s = Superresolution(1, 1, 1, 0, num_aug=10, optimizer=o, copy_dropout=0.35)
+    np.random.seed(5)
+    m1 = s._dropout_keep(10)
+    m2 = s._dropout_keep(10)           # second call must not redraw (mask is baked in at trace time, :47-53)
+    assert m1.sum() == 7 and np.array_equal(m1, m2)
+    np.random.seed(5)
+    ref = np.full(10, True); ref[:3] = False; np.random.shuffle(ref)
+    np.testing.assert_array_equal(m1.astype(bool), ref)
+    assert Superresolution(1, 1, 1, 0, num_aug=10, optimizer=o)._dropout_keep(10) is None
+
+
+def test_resize_and_iou_helpers():
+    a = np.arange(16, dtype=np.float32).reshape(4, 4, 1)
+    up = utils._resize(a, (8, 8), "bilinear")
+    ref = torch.nn.functional.interpolate(torch.from_numpy(a[None, :, :, 0])[None], size=(8, 8), mode="bilinear", align_corners=False)[0, 0].numpy()
+    np.testing.assert_allclose(up[..., 0], ref, atol=1e-6)
+    np.testing.assert_array_equal(utils._resize(a, (8, 8), "nearest")[::2, ::2], a)
+    t = np.array([[8, 8, 0, 3]]); p = np.array([[8, 0, 0, 0]])
+    assert utils.compute_IoU(t, p, img_size=(1, 4), class_id=8) == 0.5
+    assert utils.compute_IoU(t, p, img_size=(1, 4), class_id=8, include_bg=True) == pytest.approx((0.5 + 2 / 3) / 2)
+    assert np.isnan(utils.compute_IoU(np.zeros((1, 4)), np.zeros((1, 4)), img_size=(1, 4), class_id=8))
+    assert utils.create_mask(np.array([[[0.1, 0.9, 0.9]]])).tolist() == [[[1]]]
+
+
+def test_shard_bounds_cover_everything_once():
+    for n, w in ((500, 8), (500, 1), (7, 8), (64, 3), (0, 4)):
+        seen = []
+        for r in range(w):
+            a, b = sharding.shard_bounds(n, w, r)
+            seen += list(range(a, b))
+        assert seen == list(range(n))
+    assert sharding.shard_bounds(500, 8, 7) == (441, 500)
+
+
+def _gather_worker(rank, world, port, n_total, q):
+    import torch.distributed as dist
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    a, b = sharding.shard_bounds(n_total, world, rank)
+    local = torch.stack([torch.full((4, 4), i, dtype=torch.uint8) for i in range(a, b)]) if b > a else torch.zeros((0, 4, 4), dtype=torch.uint8)
+    out = sharding.gather_masks(local, n_total)
+    if rank == 0:
+        q.put(out.numpy())
+    else:
+        assert out is None
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n_total", [5, 8])
+def test_gather_masks_world_size_2_gloo(n_total):
+    import socket
+    import torch.multiprocessing as mp
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_gather_worker, args=(r, 2, port, n_total, q)) for r in range(2)]
+    [p.start() for p in procs]
+    out = q.get(timeout=120)
+    [p.join(timeout=120) for p in procs]
+    assert all(p.exitcode == 0 for p in procs)
+    assert out.shape == (n_total, 4, 4)
+    np.testing.assert_array_equal(out[:, 0, 0], np.arange(n_total))
