@@ -11,6 +11,7 @@
 // Both are gather-form (no atomics) and bit-reproduce the un-fused fp32 evaluation order of the
 // TensorFlow ops (see asr_common.cuh).  DESIGN.md derives the restructurings used here and why
 // each is bit-identical to the literal two-pass evaluation.
+#include <cuda.h>
 #include <math.h>
 #include <vector>
 
@@ -68,18 +69,20 @@ __global__ void k_init_upsample(const float* __restrict__ copies, float* __restr
 // For copy k and LR cell (i,j):  r = resize(translate(rotate(x)))[i,j] - y_k[i,j].
 // The resize reads only z at rows {4i+1,4i+2} x cols {4j+1,4j+2}; each z is a 2x2 stencil of the
 // rotated image p on integer positions, so one cell needs p on a 3x3 patch whose origin is
-// (4j+1+floor(-dx), 4i+1+floor(-dy)).  A CTA stages the x region that patch set can touch in
-// shared memory (zero filled outside the image), evaluates the 48x48 needed p values with the op's
-// exact arithmetic, then a second phase combines them per cell with per-column/row weight tables
-// that carry the literal translate weights, the zero fill of p outside the canvas, and the rare
-// rounding case where floor(fl(Z-dx)) is one above Z+floor(-dx).
+// (4j+1+floor(-dx), 4i+1+floor(-dy)).  A CTA (16x16 cells, one copy) bounds the x region those
+// patches can touch from the four corner coordinates, pulls that box into shared memory with ONE
+// TMA tensor load (cp.async.bulk.tensor; out-of-image elements arrive as zeros, which is exactly the
+// op's fill), evaluates the 48x48 needed p values with the op's arithmetic, and a second phase
+// combines them per cell with per-column/row tap tables that carry the literal translate weights,
+// the zero fill of p outside the canvas, and the rounding case floor(fl(Z-dx)) == Z+floor(-dx)+1.
 constexpr int K1_T = 16;               // LR tile edge (cells)
 constexpr int K1_THREADS = 192;        // 48 p-columns x 4 row groups
 constexpr int K1_P = 3 * K1_T;         // p positions per tile edge
 constexpr int K1_PBS = K1_P + 1;       // p buffer stride
-constexpr int K1_XS = 96;              // x tile stride (floats), multiple of 32 -> conflict-free gathers
-constexpr int K1_XR = 92;              // x tile rows: 62*sqrt(2)+3 < 92
-constexpr size_t K1_SMEM = sizeof(float) * (K1_XS * K1_XR + K1_P * K1_PBS) + sizeof(float4) * 2 * K1_T;
+constexpr int K1_XS = 96;              // TMA box width  (floats): 62*sqrt(2)+3 < 96, multiple of 32 -> conflict-free gathers
+constexpr int K1_XR = 92;              // TMA box height
+constexpr unsigned K1_BOX_BYTES = K1_XS * K1_XR * sizeof(float);
+constexpr size_t K1_SMEM = K1_BOX_BYTES + sizeof(float) * (K1_P * K1_PBS) + sizeof(float4) * 2 * K1_T;
 
 // translate stencil weights of z-column Z on the window (Z+s, Z+s+1), validity of p folded in
 __device__ __forceinline__ float2 translate_taps(int Z, float t, int s, int limit) {
@@ -94,41 +97,60 @@ __device__ __forceinline__ float2 translate_taps(int Z, float t, int s, int limi
     return make_float2(wa, wb);
 }
 
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// one 3-D tiled tensor load global -> shared, completion counted in bytes on `bar`
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, int c0, int c1, int c2, unsigned long long* bar,
+                                            unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                 ::"r"(smem_u32(dst)), "l"(reinterpret_cast<unsigned long long>(map)), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar))
+                 : "memory");
+}
+
 __global__ void __launch_bounds__(K1_THREADS)
-k_forward_residual(const float* __restrict__ x, const float* __restrict__ copies, float* __restrict__ resid,
+k_forward_residual(const __grid_constant__ CUtensorMap xmap, const float* __restrict__ copies, float* __restrict__ resid,
                    const FwdXf* __restrict__ fwd, const int* __restrict__ src_idx,
-                   const ImgParams* __restrict__ ip, int it, int N, int h, int w, int H, int W) {
+                   const ImgParams* __restrict__ ip, int it, int N, int h, int w, int H, int W, int ntj, unsigned ntj_magic,
+                   int b_base) {
     const int b = blockIdx.z, ks = blockIdx.y;
     const ImgParams P = ip[b];
     if (ks >= P.n_kept || it >= P.num_iter) return;
 
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    float* xt = reinterpret_cast<float*>(smem_raw);          // [K1_XR][K1_XS]
-    float* pb = xt + K1_XS * K1_XR;                          // [K1_P][K1_PBS]
-    float4* colw = reinterpret_cast<float4*>(pb + K1_P * K1_PBS);  // [K1_T] (w1a,w1b,w2a,w2b)
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ __align__(8) unsigned long long bar;
+    float* xt = reinterpret_cast<float*>(smem_raw);                              // [K1_XR][K1_XS], filled by TMA
+    float* pb = xt + K1_XS * K1_XR;                                              // [K1_P][K1_PBS]
+    float4* colw = reinterpret_cast<float4*>(pb + K1_P * K1_PBS);                // [K1_T] (w1a,w1b,w2a,w2b)
     float4* roww = colw + K1_T;
 
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int ntj = (w + K1_T - 1) / K1_T;
-    const int j0 = (blockIdx.x % ntj) * K1_T, i0 = (blockIdx.x / ntj) * K1_T;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int ti = (int)__umulhi(blockIdx.x, ntj_magic), tj = (int)blockIdx.x - ti * ntj;   // tile row / column
+    const int j0 = tj * K1_T, i0 = ti * K1_T;
     const FwdXf T = fwd[(size_t)b * N + ks];
     const int sx = (int)floorf(T.tx), sy = (int)floorf(T.ty);
     const int qx_lo = 4 * j0 + 1 + sx, qy_lo = 4 * i0 + 1 + sy;   // first needed p position
     constexpr int SPAN = 4 * (K1_T - 1) + 2;                      // last needed = lo + SPAN
 
-    // ---- weight tables (read only after two barriers) ------------------------------------------
-    if (tid < K1_T) {
-        const int Z1 = 4 * (j0 + tid) + 1;
-        const float2 a = translate_taps(Z1, T.tx, sx, W), c = translate_taps(Z1 + 1, T.tx, sx, W);
-        colw[tid] = make_float4(a.x, a.y, c.x, c.y);
-    } else if (tid >= 32 && tid < 32 + K1_T) {
-        const int Z1 = 4 * (i0 + tid - 32) + 1;
-        const float2 a = translate_taps(Z1, T.ty, sy, H), c = translate_taps(Z1 + 1, T.ty, sy, H);
-        roww[tid - 32] = make_float4(a.x, a.y, c.x, c.y);
-    }
+    if (tid == 0) mbar_init(&bar, 1);
 
-    // ---- source bounding box of the p region: extremes are at the corners (each rounded op is
-    //      monotone in qx and in qy), so the literal coordinates of the corners bound all taps ----
+    // ---- source bounding box of the p region: each rounded op of the coordinate is monotone in qx
+    //      and in qy, so the literal coordinates of the four corners bound every tap -----------------
     float cix, ciy;
     {
         const float qx = (float)(qx_lo + ((lane & 1) ? SPAN : 0)), qy = (float)(qy_lo + ((lane & 2) ? SPAN : 0));
@@ -137,42 +159,51 @@ k_forward_residual(const float* __restrict__ x, const float* __restrict__ copies
     }
     const int bx0 = (int)floorf(warp_min(cix)), bx1 = (int)floorf(warp_max(cix)) + 1;
     const int by0 = (int)floorf(warp_min(ciy)), by1 = (int)floorf(warp_max(ciy)) + 1;
+    // TMA needs the innermost start coordinate 16-byte aligned (an unaligned start faults with
+    // "illegal instruction" on B200: scripts/dev/tma_test3.cu), so the box starts at bx0 rounded down to 4
     const int bx0a = bx0 & ~3;
-    const int ncol4 = ((bx1 - bx0a) >> 2) + 1, nrow = by1 - by0 + 1;
-    if (ncol4 * 4 > K1_XS || nrow > K1_XR) return;  // cannot happen for a rotation (host checks |r0|+|r1|)
-
+    if (bx1 - bx0a >= K1_XS || by1 - by0 >= K1_XR) return;  // cannot happen for a rotation (box <= 62*sqrt(2)+2+3)
     const bool empty = (bx1 < 0 || bx0 >= W || by1 < 0 || by0 >= H);  // rotated image is all zero here
-    if (!empty) {
-        // ---- stage x[by0..by1][bx0a..] with zero fill --------------------------------------------
-        const float* xb = x + (size_t)b * H * W;
-        for (int row = warp; row < nrow; row += K1_THREADS / 32) {
-            const int gy = by0 + row;
-            if (lane < ncol4) {
-                const int gx = bx0a + 4 * lane;
-                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (gy >= 0 && gy < H && gx >= 0 && gx < W) v = __ldg(reinterpret_cast<const float4*>(xb + (size_t)gy * W + gx));
-                *reinterpret_cast<float4*>(xt + row * K1_XS + 4 * lane) = v;
-            }
-        }
-        __syncthreads();
 
+    __syncthreads();                                               // barrier init visible
+    if (tid == 0 && !empty) tma_load_3d(xt, &xmap, bx0a, by0, b_base + b, &bar, K1_BOX_BYTES);
+
+    // ---- tap tables, overlapped with the TMA flight (read after the next __syncthreads) ---------
+    if (tid >= 64 && tid < 64 + K1_T) {
+        const int c = tid - 64, Z1 = 4 * (j0 + c) + 1;
+        const float2 a = translate_taps(Z1, T.tx, sx, W), d = translate_taps(Z1 + 1, T.tx, sx, W);
+        colw[c] = make_float4(a.x, a.y, d.x, d.y);
+    } else if (tid >= 96 && tid < 96 + K1_T) {
+        const int c = tid - 96, Z1 = 4 * (i0 + c) + 1;
+        const float2 a = translate_taps(Z1, T.ty, sy, H), d = translate_taps(Z1 + 1, T.ty, sy, H);
+        roww[c] = make_float4(a.x, a.y, d.x, d.y);
+    }
+
+    if (!empty) {
         // ---- p = rotate-gather of x at the needed integer positions ------------------------------
         const int pcn = tid % K1_P, g = tid / K1_P;               // p column, row group (12 rows each)
         const int qx = qx_lo + 4 * (pcn / 3) + (pcn % 3);
         const float qxf = (float)qx;
         const float ax = fmul(T.r0, qxf), ay = fmul(T.r3, qxf);
         const float qyf0 = (float)(qy_lo + 16 * g);
-        const unsigned cst = 0u - (unsigned)(kMagicBits + by0) * K1_XS - (unsigned)(kMagicBits + bx0a);
+        // word offset of tap (y0,x0) = raw_y*XS + raw_x + cst (mod 2^32); kept opaque so that the compiler
+        // cannot split the magic constant out of it and re-add it once per tap
+        unsigned cst = 0u - (unsigned)(kMagicBits + by0) * K1_XS - (unsigned)(kMagicBits + bx0a);
+        asm volatile("" : "+r"(cst));
+        float* prow = pb + (12 * g) * K1_PBS + pcn;
+        mbar_wait(&bar, 0);
 #pragma unroll
         for (int m = 0; m < 12; ++m) {
             const float qyf = qyf0 + (float)(4 * (m / 3) + (m % 3));   // exact small-integer add
             const float ix = fadd(fadd(ax, fmul(T.r1, qyf)), T.r2);
             const float iy = fadd(fadd(ay, fmul(T.r4, qyf)), T.r5);
             const Floor fx = floor_magic(ix), fy = floor_magic(iy);
-            const float wx0 = fsub(fadd(fx.f, 1.0f), ix), wx1 = fsub(ix, fx.f);
-            const float wy0 = fsub(fadd(fy.f, 1.0f), iy), wy1 = fsub(iy, fy.f);
-            const float* t0 = xt + ((unsigned)fy.raw * K1_XS + (unsigned)fx.raw + cst);   // wraps mod 2^32 to the tile offset
-            pb[(12 * g + m) * K1_PBS + pcn] = bilerp(t0[0], t0[1], t0[K1_XS], t0[K1_XS + 1], wx0, wx1, wy0, wy1);
+            // (x_ceil - x) == 1 - (x - x_floor) bit for bit unless x in (-1,0), where that weight only ever
+            // multiplies the out-of-image tap x_floor = -1, i.e. an exact zero
+            const float wx1 = fsub(ix, fx.f), wx0 = fsub(1.0f, wx1);
+            const float wy1 = fsub(iy, fy.f), wy0 = fsub(1.0f, wy1);
+            const float* t0 = xt + ((unsigned)fy.raw * K1_XS + ((unsigned)fx.raw + cst));
+            prow[m * K1_PBS] = bilerp(t0[0], t0[1], t0[K1_XS], t0[K1_XS + 1], wx0, wx1, wy0, wy1);
         }
     }
     __syncthreads();
@@ -257,7 +288,7 @@ k_gradient_update(const float* __restrict__ x_cur, float* __restrict__ x_next, f
     const ImgParams P = ip[b];
     if (it >= P.num_iter) return;
 
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     float* ut = reinterpret_cast<float*>(smem_raw);                       // [2][K2_UR][K2_US]
     float2* colw = reinterpret_cast<float2*>(ut + 2 * K2_US * K2_UR);     // [2][K2_US]
     float2* roww = colw + 2 * K2_US;                                      // [2][K2_UR]
@@ -349,6 +380,8 @@ k_gradient_update(const float* __restrict__ x_cur, float* __restrict__ x_next, f
             const KBox bx = boxes[step & 3];
             if (!bx.skip) {
                 const InvXf T = invb[step];
+                unsigned cst = bx.cst;
+                asm volatile("" : "+r"(cst));
                 float ax[2], ay[2], bxr[4], byr[4];
 #pragma unroll
                 for (int c = 0; c < 2; ++c) { ax[c] = fmul(T.b0, Xf[c]); ay[c] = fmul(T.b3, Xf[c]); }
@@ -361,9 +394,11 @@ k_gradient_update(const float* __restrict__ x_cur, float* __restrict__ x_next, f
                         const float ix = fadd(fadd(ax[c], bxr[r]), T.b2);
                         const float iy = fadd(fadd(ay[c], byr[r]), T.b5);
                         const Floor fx = floor_magic(ix), fy = floor_magic(iy);
-                        const float wx0 = fsub(fadd(fx.f, 1.0f), ix), wx1 = fsub(ix, fx.f);
-                        const float wy0 = fsub(fadd(fy.f, 1.0f), iy), wy1 = fsub(iy, fy.f);
-                        const float* t0 = ut + ((unsigned)fy.raw * K2_US + (unsigned)fx.raw + bx.cst);
+                        // (x_ceil - x) == 1 - (x - x_floor) bit for bit unless x in (-1,0), where that weight only
+                        // multiplies the tap x_floor = -1, which lies outside the canvas and is an exact zero of u
+                        const float wx1 = fsub(ix, fx.f), wx0 = fsub(1.0f, wx1);
+                        const float wy1 = fsub(iy, fy.f), wy0 = fsub(1.0f, wy1);
+                        const float* t0 = ut + ((unsigned)fy.raw * K2_US + ((unsigned)fx.raw + cst));
                         acc[2 * r + c] = fadd(acc[2 * r + c], bilerp(t0[0], t0[1], t0[K2_US], t0[K2_US + 1], wx0, wx1, wy0, wy1));
                     }
                 }
@@ -644,6 +679,32 @@ static int upload(const HostTables& T, const Device& D, cudaStream_t st) {
     return ASR_OK;
 }
 
+// 3-D tiled tensor map over an x buffer [B][H][W] fp32 with the K1 box; out-of-bounds elements read as zero
+static int make_x_map(CUtensorMap* map, const float* base, int B, int H, int W) {
+    typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                 const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static EncodeFn encode = nullptr;
+    if (!encode) {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        ASR_CUDA_TRY(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q));
+        if (!fn || q != cudaDriverEntryPointSuccess) return fail(ASR_ECUDA, "cuTensorMapEncodeTiled is not available in this driver");
+        encode = reinterpret_cast<EncodeFn>(fn);
+    }
+    const cuuint64_t gdim[3] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+    const cuuint64_t gstride[2] = {(cuuint64_t)W * sizeof(float), (cuuint64_t)W * H * sizeof(float)};
+    const cuuint32_t box[3] = {K1_XS, K1_XR, 1};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    const CUresult r = encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), gdim, gstride, box, estr,
+                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(ASR_ECUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+    return ASR_OK;
+}
+
+static unsigned div_magic(int d) { return (unsigned)((0x100000000ull + (unsigned)d - 1) / (unsigned)d); }   // __umulhi(n, magic) == n / d for n*d < 2^32
+
 static int configure_kernels() {
     static bool done = false;   // attribute is per-function, idempotent; a benign race at worst repeats it
     if (done) return ASR_OK;
@@ -698,8 +759,12 @@ extern "C" int asr_solve_batched(const AsrSolveParams* params, int n_params, con
             ASR_LAUNCH(k_fill, 64, 256, 0, st, D.s0 + (size_t)b * plane, T.hp[b].initial_accumulator_value, plane);
     ASR_LAUNCH(k_init_upsample, dim3((W + 31) / 32, (H + 7) / 8, B), dim3(32, 8), 0, st, d_copies, D.xa, N, h, w, H, W);
 
-    const int t1 = ((w + K1_T - 1) / K1_T) * ((h + K1_T - 1) / K1_T);
+    const int ntj = (w + K1_T - 1) / K1_T;
+    const int t1 = ntj * ((h + K1_T - 1) / K1_T);
     const int t2 = ((W + K2_T - 1) / K2_T) * ((H + K2_T - 1) / K2_T);
+    CUtensorMap map_a, map_b;
+    if (int e = make_x_map(&map_a, D.xa, B, H, W)) return e;
+    if (int e = make_x_map(&map_b, D.xb, B, H, W)) return e;
     int group = params[0].images_in_flight > 0 ? params[0].images_in_flight : B;
     for (int b0 = 0; b0 < B; b0 += group) {
         const int nb = (B - b0 < group) ? B - b0 : group;
@@ -709,8 +774,9 @@ extern "C" int asr_solve_batched(const AsrSolveParams* params, int n_params, con
         for (int it = 0; it < iters; ++it) {
             float* xc = ((it & 1) ? D.xb : D.xa) + po;
             float* xn = ((it & 1) ? D.xa : D.xb) + po;
-            ASR_LAUNCH_TIMED(0, k_forward_residual, dim3(t1, T.max_kept, nb), K1_THREADS, K1_SMEM, st, 
-                xc, d_copies + ro, D.resid + ro, D.fwd + (size_t)b0 * N, D.src + (size_t)b0 * N, D.ip + b0, it, N, h, w, H, W);
+            ASR_LAUNCH_TIMED(0, k_forward_residual, dim3(t1, T.max_kept, nb), K1_THREADS, K1_SMEM, st,
+                (it & 1) ? map_b : map_a, d_copies + ro, D.resid + ro, D.fwd + (size_t)b0 * N, D.src + (size_t)b0 * N, D.ip + b0,
+                it, N, h, w, H, W, ntj, div_magic(ntj), b0);
             ASR_LAUNCH_TIMED(1, (k_gradient_update<false>), dim3(t2, nb), K2_THREADS, K2_SMEM, st, 
                 xc, xn, D.s0 + po, D.s1 + po, D.s2 + po, D.resid + ro, D.inv + (size_t)b0 * N, D.ip + b0,
                 D.sched + b0, it, N, h, w, H, W, B);
@@ -747,9 +813,13 @@ extern "C" int asr_loss_grad_batched(const AsrSolveParams* params, int n_params,
 
     const size_t plane = (size_t)H * W;
     ASR_CUDA_TRY(cudaMemcpyAsync(D.xa, d_x, sizeof(float) * B * plane, cudaMemcpyDeviceToDevice, st));
-    const int t1 = ((w + K1_T - 1) / K1_T) * ((h + K1_T - 1) / K1_T);
+    const int ntj = (w + K1_T - 1) / K1_T;
+    const int t1 = ntj * ((h + K1_T - 1) / K1_T);
     const int t2 = ((W + K2_T - 1) / K2_T) * ((H + K2_T - 1) / K2_T);
-    ASR_LAUNCH_TIMED(0, k_forward_residual, dim3(t1, T.max_kept, B), K1_THREADS, K1_SMEM, st, D.xa, d_copies, D.resid, D.fwd, D.src, D.ip, 0, N, h, w, H, W);
+    CUtensorMap map_a;
+    if (int e = make_x_map(&map_a, D.xa, B, H, W)) return e;
+    ASR_LAUNCH_TIMED(0, k_forward_residual, dim3(t1, T.max_kept, B), K1_THREADS, K1_SMEM, st, map_a, d_copies, D.resid, D.fwd, D.src, D.ip,
+                     0, N, h, w, H, W, ntj, div_magic(ntj), 0);
     ASR_LAUNCH_TIMED(1, (k_gradient_update<true>), dim3(t2, B), K2_THREADS, K2_SMEM, st, D.xa, D.xb, D.s0, D.s1, D.s2, D.resid, D.inv, D.ip,
                                                                       D.sched, 0, N, h, w, H, W, B);
     ASR_CUDA_TRY(cudaGetLastError());
