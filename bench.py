@@ -103,6 +103,7 @@ class ClockSampler:
 # ---------------------------------------------------------------------------------------------------------------
 def oracle_sample(copies_np, ang, sh, iters):
     from oracle import oracle as O
+    O.use_all_cores()
     P = O.SolveParams(num_iter=int(iters))
     t = time.perf_counter()
     O.augmented_superresolution(copies_np, ang, sh, P, output_size=HR_HW)
@@ -113,7 +114,7 @@ def oracle_sample(copies_np, ang, sh, iters):
 def cpu_baseline(copies_np, ang, sh, budget_s):
     dt3, cores = oracle_sample(copies_np, ang, sh, 3)
     per_iter = dt3 / 3
-    n = int(max(5, min(60, budget_s / per_iter)))
+    n = int(max(5, min(150, budget_s / per_iter)))
     dt, cores = oracle_sample(copies_np, ang, sh, n)
     per_iter = dt / n
     return {"value": 1.0 / (per_iter * ITERS), "unit": UNIT, "cores": cores, "kind": "port",

@@ -250,22 +250,25 @@ k_forward_residual(const __grid_constant__ CUtensorMap xmap, const float* __rest
 // positions that cell feeds (q+floor(d) in [4c,4c+3]); the block's values follow the literal 2-tap
 // sums, which collapse to w_b*g / (w_a*g + w_b*g) / w_a*g / 0 by phase because the other tap reads
 // an exact zero.  Every thread then gathers 8 pixels from that tile with the op's exact arithmetic
-// and adds them to its accumulators in ascending copy order.  Stages for copies k+3 (box), k+2
-// (weight tables), k+1 (u tile) and k (gather) run in one barrier interval.
+// and adds them to its accumulators in ascending copy order.
+// Schedule: bounding boxes and the inverse transforms of a chunk of 128 copies are computed once
+// into shared memory (one thread per copy), then each barrier interval runs, for copies k+2 / k+1 / k:
+// tap tables, u-tile fill (its residual load is prefetched before the gather) and the gather.
 constexpr int K2_T = 64;               // HR tile edge
 constexpr int K2_THREADS = 512;        // 16 warps; thread owns pixels (lane + 32c, warp + 16r), c<2, r<4
 constexpr int K2_US = 96;              // u tile stride: 64*sqrt(2)+2+3 < 96, multiple of 32
 constexpr int K2_UR = 96;              // u tile rows
-struct KBox {
-    unsigned cst;   // word offset folding the magic bias, the box origin and the buffer (mod 2^32)
-    int skip;       // box does not touch the LR grid: u == 0
+constexpr int K2_CHUNK = 128;          // copies whose boxes/transforms are staged at once
+struct __align__(16) KBox {
+    unsigned cst;   // word offset folding the magic bias and the box origin (mod 2^32), buffer offset excluded
     int cbx0, cby0; // first LR cell of the box
-    int ncx, ncy;   // cells per box edge
+    int ncxy;       // ncx | ncy << 8 | skip << 16   (skip: box does not touch the LR grid, u == 0)
     int qx_lo, qy_lo;
     int inv_ncx;    // ceil(65536 / ncx) for the cell index split
-    int pad[3];
+    int pad;
 };
-constexpr size_t K2_SMEM = sizeof(float) * 2 * K2_US * K2_UR + sizeof(float2) * 2 * (K2_US + K2_UR) + sizeof(KBox) * 4;
+constexpr size_t K2_SMEM = sizeof(float) * 2 * K2_US * K2_UR + sizeof(float2) * 2 * (K2_US + K2_UR) +
+                           (sizeof(KBox) + sizeof(InvXf)) * K2_CHUNK;
 
 // literal taps of the inverse-translate gather on the window (q+s, q+s+1).  u_k is an image on the
 // HR canvas: the rotate-gradient gather zero-fills q outside [0,limit), so those columns/rows get
@@ -292,7 +295,8 @@ k_gradient_update(const float* __restrict__ x_cur, float* __restrict__ x_next, f
     float* ut = reinterpret_cast<float*>(smem_raw);                       // [2][K2_UR][K2_US]
     float2* colw = reinterpret_cast<float2*>(ut + 2 * K2_US * K2_UR);     // [2][K2_US]
     float2* roww = colw + 2 * K2_US;                                      // [2][K2_UR]
-    KBox* boxes = reinterpret_cast<KBox*>(roww + 2 * K2_UR);              // [4]
+    KBox* boxes = reinterpret_cast<KBox*>(roww + 2 * K2_UR);              // [K2_CHUNK]
+    InvXf* xfs = reinterpret_cast<InvXf*>(boxes + K2_CHUNK);              // [K2_CHUNK]
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int ntx = (W + K2_T - 1) / K2_T;
@@ -300,6 +304,9 @@ k_gradient_update(const float* __restrict__ x_cur, float* __restrict__ x_next, f
     const InvXf* invb = inv + (size_t)b * N;
     const float* rb = resid + (size_t)b * N * h * w;
     const int nk = P.n_kept;
+    // u-tile cells are spread over the threads starting at warp 6, so that warps 0-5, which also
+    // build the tap tables, get at most a few cells: every warp does a similar amount per interval
+    const int fill_slot = (tid + K2_THREADS - (K2_US + K2_UR)) & (K2_THREADS - 1);
 
     float Xf[2], Yf[4], acc[8];
 #pragma unroll
@@ -309,57 +316,108 @@ k_gradient_update(const float* __restrict__ x_cur, float* __restrict__ x_next, f
 #pragma unroll
     for (int e = 0; e < 8; ++e) acc[e] = 0.0f;
 
-    for (int step = -3; step < nk; ++step) {
-        // ---- stage A: bounding box of copy step+3 (warp 15, lanes 0-3 = tile corners) --------------
-        if (warp == 15 && step + 3 < nk) {
-            const int kk = step + 3;
-            const InvXf T = invb[kk];
-            const float X = (float)(tx0 + ((lane & 1) ? K2_T - 1 : 0)), Y = (float)(ty0 + ((lane & 2) ? K2_T - 1 : 0));
-            const float cix = affine_coord(T.b0, X, T.b1, Y, T.b2), ciy = affine_coord(T.b3, X, T.b4, Y, T.b5);
-            const int qx0 = (int)floorf(warp_min(cix)), qx1 = (int)floorf(warp_max(cix)) + 1;
-            const int qy0 = (int)floorf(warp_min(ciy)), qy1 = (int)floorf(warp_max(ciy)) + 1;
-            if (lane == 0) {
-                const int sx = (int)floorf(T.ux), sy = (int)floorf(T.uy);
-                KBox bx;
-                bx.cbx0 = (qx0 + sx) >> LOG2S;
-                bx.cby0 = (qy0 + sy) >> LOG2S;
-                const int cbx1 = (qx1 + sx) >> LOG2S, cby1 = (qy1 + sy) >> LOG2S;
-                bx.ncx = cbx1 - bx.cbx0 + 1;
-                bx.ncy = cby1 - bx.cby0 + 1;
-                bx.qx_lo = 4 * bx.cbx0 - sx;
-                bx.qy_lo = 4 * bx.cby0 - sy;
-                bx.skip = (cbx1 < 0 || bx.cbx0 >= w || cby1 < 0 || bx.cby0 >= h || 4 * bx.ncx > K2_US || 4 * bx.ncy > K2_UR);
-                bx.cst = (unsigned)((kk & 1) * (K2_US * K2_UR)) - (unsigned)(kMagicBits + bx.qy_lo) * K2_US -
-                         (unsigned)(kMagicBits + bx.qx_lo);
-                bx.inv_ncx = (65536 + bx.ncx - 1) / bx.ncx;
-                boxes[kk & 3] = bx;
+    for (int k0 = 0; k0 < nk; k0 += K2_CHUNK) {
+        const int nc = min(K2_CHUNK, nk - k0);
+        __syncthreads();   // the previous chunk's boxes are no longer read
+        // ---- chunk prologue: bounding box of Rinv(tile) for each copy (one thread per copy).  Each
+        //      rounded op of the coordinate is monotone in X and Y: the four corners bound every tap.
+        if (tid < nc) {
+            const InvXf T = invb[k0 + tid];
+            float xmin = INFINITY, xmax = -INFINITY, ymin = INFINITY, ymax = -INFINITY;
+#pragma unroll
+            for (int cnr = 0; cnr < 4; ++cnr) {
+                const float X = (float)(tx0 + ((cnr & 1) ? K2_T - 1 : 0)), Y = (float)(ty0 + ((cnr & 2) ? K2_T - 1 : 0));
+                const float cix = affine_coord(T.b0, X, T.b1, Y, T.b2), ciy = affine_coord(T.b3, X, T.b4, Y, T.b5);
+                xmin = fminf(xmin, cix); xmax = fmaxf(xmax, cix); ymin = fminf(ymin, ciy); ymax = fmaxf(ymax, ciy);
             }
+            const int qx0 = (int)floorf(xmin), qx1 = (int)floorf(xmax) + 1, qy0 = (int)floorf(ymin), qy1 = (int)floorf(ymax) + 1;
+            const int sx = (int)floorf(T.ux), sy = (int)floorf(T.uy);
+            KBox bx;
+            bx.cbx0 = (qx0 + sx) >> LOG2S;
+            bx.cby0 = (qy0 + sy) >> LOG2S;
+            const int cbx1 = (qx1 + sx) >> LOG2S, cby1 = (qy1 + sy) >> LOG2S;
+            const int ncx = cbx1 - bx.cbx0 + 1, ncy = cby1 - bx.cby0 + 1;
+            bx.qx_lo = 4 * bx.cbx0 - sx;
+            bx.qy_lo = 4 * bx.cby0 - sy;
+            const int skip = (cbx1 < 0 || bx.cbx0 >= w || cby1 < 0 || bx.cby0 >= h || 4 * ncx > K2_US || 4 * ncy > K2_UR);
+            bx.ncxy = (ncx & 0xff) | ((ncy & 0xff) << 8) | (skip << 16);
+            bx.cst = 0u - (unsigned)(kMagicBits + bx.qy_lo) * K2_US - (unsigned)(kMagicBits + bx.qx_lo);
+            bx.inv_ncx = (65536 + ncx - 1) / max(ncx, 1);
+            bx.pad = 0;
+            boxes[tid] = bx;
+            xfs[tid] = T;
         }
-        // ---- stage B: literal translate weights of copy step+2 for every q column / row of its box --
-        if (step + 2 >= 0 && step + 2 < nk && tid < K2_US + K2_UR) {
-            const int kk = step + 2;
-            const KBox bx = boxes[kk & 3];
-            if (!bx.skip) {
-                const InvXf T = invb[kk];
-                if (tid < K2_US) colw[(kk & 1) * K2_US + tid] = inv_translate_taps(bx.qx_lo + tid, T.ux, (int)floorf(T.ux), W);
-                else roww[(kk & 1) * K2_UR + tid - K2_US] = inv_translate_taps(bx.qy_lo + tid - K2_US, T.uy, (int)floorf(T.uy), H);
+        __syncthreads();
+
+        for (int step = -2; step < nc; ++step) {
+            // ---- u-tile cell of copy step+1 owned by this thread: issue its residual load early --------
+            const int kc = step + 1;
+            int cell_off = -1, cyi = 0, cxi = 0;
+            float r_pref = 0.0f;
+            bool do_fill = false;
+            KBox bc;
+            if (kc >= 0 && kc < nc) {
+                bc = boxes[kc];
+                const int ncx = bc.ncxy & 0xff, ncy = (bc.ncxy >> 8) & 0xff;
+                do_fill = !(bc.ncxy >> 16) && fill_slot < ncx * ncy;
+                if (do_fill) {
+                    cyi = (fill_slot * bc.inv_ncx) >> 16;
+                    cxi = fill_slot - cyi * ncx;
+                    const int cy = bc.cby0 + cyi, cx = bc.cbx0 + cxi;
+                    if (cy >= 0 && cy < h && cx >= 0 && cx < w) {
+                        cell_off = ((k0 + kc) * h + cy) * w + cx;
+                        asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(r_pref) : "l"(rb + cell_off));   // consumed after the gather
+                    }
+                }
             }
-        }
-        // ---- stage C: u tile of copy step+1, one thread per LR cell -> 4x4 block ---------------------
-        if (step + 1 >= 0 && step + 1 < nk) {
-            const int kk = step + 1;
-            const KBox bx = boxes[kk & 3];
-            if (!bx.skip) {
-                float* u = ut + (kk & 1) * (K2_US * K2_UR);
-                const float4* cw4 = reinterpret_cast<const float4*>(colw + (kk & 1) * K2_US);
-                const float4* rw4 = reinterpret_cast<const float4*>(roww + (kk & 1) * K2_UR);
-                const float* rk = rb + (size_t)kk * h * w;
-                const int ncell = bx.ncx * bx.ncy;
-                for (int c = tid; c < ncell; c += K2_THREADS) {
-                    const int cyi = (c * bx.inv_ncx) >> 16, cxi = c - cyi * bx.ncx;
-                    const int cy = bx.cby0 + cyi, cx = bx.cbx0 + cxi;
-                    float r = 0.0f;
-                    if (cy >= 0 && cy < h && cx >= 0 && cx < w) r = __ldg(rk + cy * w + cx);
+            // ---- literal translate weights of copy step+2 for every q column / row of its box ----------
+            const int kt = step + 2;
+            if (kt < nc && tid < K2_US + K2_UR) {
+                const KBox bx = boxes[kt];
+                if (!(bx.ncxy >> 16)) {
+                    const float ux = xfs[kt].ux, uy = xfs[kt].uy;
+                    if (tid < K2_US) colw[(kt & 1) * K2_US + tid] = inv_translate_taps(bx.qx_lo + tid, ux, (int)floorf(ux), W);
+                    else roww[(kt & 1) * K2_UR + tid - K2_US] = inv_translate_taps(bx.qy_lo + tid - K2_US, uy, (int)floorf(uy), H);
+                }
+            }
+            // ---- gather copy `step` into the accumulators (ascending copy order) ------------------------
+            if (step >= 0) {
+                const KBox bx = boxes[step];
+                if (!(bx.ncxy >> 16)) {
+                    const InvXf T = xfs[step];
+                    unsigned cst = bx.cst + (unsigned)((step & 1) * (K2_US * K2_UR));
+                    asm volatile("" : "+r"(cst));   // opaque: keeps the address math at IADD + IMAD + LEA
+                    float ax[2], ay[2], bxr[4], byr[4];
+#pragma unroll
+                    for (int c = 0; c < 2; ++c) { ax[c] = fmul(T.b0, Xf[c]); ay[c] = fmul(T.b3, Xf[c]); }
+#pragma unroll
+                    for (int r = 0; r < 4; ++r) { bxr[r] = fmul(T.b1, Yf[r]); byr[r] = fmul(T.b4, Yf[r]); }
+#pragma unroll
+                    for (int r = 0; r < 4; ++r) {
+#pragma unroll
+                        for (int c = 0; c < 2; ++c) {
+                            const float ix = fadd(fadd(ax[c], bxr[r]), T.b2);
+                            const float iy = fadd(fadd(ay[c], byr[r]), T.b5);
+                            const Floor fx = floor_magic(ix), fy = floor_magic(iy);
+                            // (x_ceil - x) == 1 - (x - x_floor) bit for bit unless x in (-1,0), where that weight only
+                            // multiplies the tap x_floor = -1, which lies outside the canvas and is an exact zero of u
+                            const float wx1 = fsub(ix, fx.f), wx0 = fsub(1.0f, wx1);
+                            const float wy1 = fsub(iy, fy.f), wy0 = fsub(1.0f, wy1);
+                            const float* t0 = ut + ((unsigned)fy.raw * K2_US + ((unsigned)fx.raw + cst));
+                            acc[2 * r + c] = fadd(acc[2 * r + c], bilerp(t0[0], t0[1], t0[K2_US], t0[K2_US + 1], wx0, wx1, wy0, wy1));
+                        }
+                    }
+                }
+            }
+            // ---- u tile of copy step+1: this thread's LR cell -> 4x4 block (boxes of more than 512 cells,
+            //      i.e. rotations near 45 degrees, give some threads a second, un-prefetched cell) ----------
+            if (do_fill) {
+                float* u = ut + (kc & 1) * (K2_US * K2_UR);
+                const float4* cw4 = reinterpret_cast<const float4*>(colw + (kc & 1) * K2_US);
+                const float4* rw4 = reinterpret_cast<const float4*>(roww + (kc & 1) * K2_UR);
+                const int ncx = bc.ncxy & 0xff, ncell = ncx * ((bc.ncxy >> 8) & 0xff);
+                float r = r_pref;
+                for (int c = fill_slot;;) {
                     const float g = fmul(0.25f, fmul(P.two_ldf, r));          // g_hr on the cell's 2x2 positions
                     const float4 ca = cw4[2 * cxi], cb = cw4[2 * cxi + 1];     // (wa0,wb0,wa1,wb1) (wa2,wb2,wa3,wb3)
                     const float t0 = fmul(ca.y, g);                           // phase 0: taps (0, g)
@@ -372,39 +430,16 @@ k_gradient_update(const float* __restrict__ x_cur, float* __restrict__ x_next, f
                                                  fadd(fmul(ra.z, t2), fmul(ra.w, t2)), 0.0f);
                     dst[2 * (K2_US / 4)] = make_float4(fmul(rc.x, t0), fmul(rc.x, t1), fmul(rc.x, t2), 0.0f);
                     dst[3 * (K2_US / 4)] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+                    c += K2_THREADS;
+                    if (c >= ncell) break;
+                    cyi = (c * bc.inv_ncx) >> 16;
+                    cxi = c - cyi * ncx;
+                    const int cy = bc.cby0 + cyi, cx = bc.cbx0 + cxi;
+                    r = (cy >= 0 && cy < h && cx >= 0 && cx < w) ? __ldg(rb + ((k0 + kc) * h + cy) * w + cx) : 0.0f;
                 }
             }
+            __syncthreads();
         }
-        // ---- stage D: gather copy `step` into the accumulators (ascending copy order) -----------------
-        if (step >= 0) {
-            const KBox bx = boxes[step & 3];
-            if (!bx.skip) {
-                const InvXf T = invb[step];
-                unsigned cst = bx.cst;
-                asm volatile("" : "+r"(cst));
-                float ax[2], ay[2], bxr[4], byr[4];
-#pragma unroll
-                for (int c = 0; c < 2; ++c) { ax[c] = fmul(T.b0, Xf[c]); ay[c] = fmul(T.b3, Xf[c]); }
-#pragma unroll
-                for (int r = 0; r < 4; ++r) { bxr[r] = fmul(T.b1, Yf[r]); byr[r] = fmul(T.b4, Yf[r]); }
-#pragma unroll
-                for (int r = 0; r < 4; ++r) {
-#pragma unroll
-                    for (int c = 0; c < 2; ++c) {
-                        const float ix = fadd(fadd(ax[c], bxr[r]), T.b2);
-                        const float iy = fadd(fadd(ay[c], byr[r]), T.b5);
-                        const Floor fx = floor_magic(ix), fy = floor_magic(iy);
-                        // (x_ceil - x) == 1 - (x - x_floor) bit for bit unless x in (-1,0), where that weight only
-                        // multiplies the tap x_floor = -1, which lies outside the canvas and is an exact zero of u
-                        const float wx1 = fsub(ix, fx.f), wx0 = fsub(1.0f, wx1);
-                        const float wy1 = fsub(iy, fy.f), wy0 = fsub(1.0f, wy1);
-                        const float* t0 = ut + ((unsigned)fy.raw * K2_US + ((unsigned)fx.raw + cst));
-                        acc[2 * r + c] = fadd(acc[2 * r + c], bilerp(t0[0], t0[1], t0[K2_US], t0[K2_US + 1], wx0, wx1, wy0, wy1));
-                    }
-                }
-            }
-        }
-        __syncthreads();
     }
 
     // ---- epilogue: TV (tf.image.image_gradients), L2, L1, optimizer ---------------

@@ -44,6 +44,7 @@ typedef struct {
 } orc_params;
 
 int orc_num_threads(void);
+void orc_set_num_threads(int n);   /* launchers such as torchrun export OMP_NUM_THREADS=1 */
 
 /* tfa.image.angles_to_projective_transforms / translations_to_projective_transforms */
 void orc_rotate_matrix(float angle, int H, int W, float t[8]);

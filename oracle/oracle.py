@@ -100,6 +100,13 @@ def num_threads() -> int:
     return lib().orc_num_threads()
 
 
+def use_all_cores() -> int:
+    """Give the oracle every core this process may run on (torchrun exports OMP_NUM_THREADS=1)."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    lib().orc_set_num_threads(int(n))
+    return num_threads()
+
+
 def rotate_matrix(angle, H, W):
     t = np.zeros(8, np.float32)
     lib().orc_rotate_matrix(C.c_float(angle), H, W, _f(t))
