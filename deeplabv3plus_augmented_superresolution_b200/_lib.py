@@ -66,6 +66,7 @@ SIGNATURES = {
     "asr_minmax_normalize": (C.c_int, [C.c_void_p, C.c_int64, C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p]),
     "asr_threshold": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, C.c_int32, C.c_float, C.c_void_p, C.c_void_p,
                                 C.c_void_p, C.c_void_p]),
+    "asr_iou_counts": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "asr_solve_batched_dlpack": (C.c_int, [C.POINTER(AsrSolveParams), C.c_int, C.c_void_p, _fp, _fp, _u8p,
                                            C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
 }

@@ -285,9 +285,48 @@ k_backproject(const float* __restrict__ copies, const BackXf* __restrict__ xf, f
     out[((size_t)b * H + Y) * W + X] = accv;
 }
 
+// ================================================================================================
+// single_class_IOU counts (utils.py:180-204): per image inter/union for `class_id` and, with
+// include_bg, for class 0 after relabelling every other ground-truth class to background
+// ================================================================================================
+__global__ void k_iou_counts(const int* __restrict__ yt, const int* __restrict__ yp, size_t n, int class_id, int include_bg,
+                             unsigned long long* __restrict__ counts) {
+    const int b = blockIdx.y;
+    const int* t = yt + (size_t)b * n;
+    const int* p = yp + (size_t)b * n;
+    unsigned ic = 0, uc = 0, ib = 0, ub = 0;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        int tv = t[i];
+        const int pv = p[i];
+        if (include_bg && tv != class_id) tv = 0;
+        const bool tc = tv == class_id, pc = pv == class_id, tb = tv == 0, pbk = pv == 0;
+        ic += tc && pc; uc += tc || pc; ib += tb && pbk; ub += tb || pbk;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        ic += __shfl_xor_sync(0xffffffffu, ic, o); uc += __shfl_xor_sync(0xffffffffu, uc, o);
+        ib += __shfl_xor_sync(0xffffffffu, ib, o); ub += __shfl_xor_sync(0xffffffffu, ub, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicAdd(counts + 4 * b + 0, (unsigned long long)ic); atomicAdd(counts + 4 * b + 1, (unsigned long long)uc);
+        atomicAdd(counts + 4 * b + 2, (unsigned long long)ib); atomicAdd(counts + 4 * b + 3, (unsigned long long)ub);
+    }
+}
+
 }  // namespace asr
 
 using namespace asr;
+
+extern "C" int asr_iou_counts(const int32_t* d_true, const int32_t* d_pred, int B, int64_t n, int class_id, int include_bg,
+                              unsigned long long* d_counts, void* stream) {
+    if (!d_true || !d_pred || !d_counts) return fail(ASR_ENULL, "null argument");
+    if (B <= 0 || n <= 0 || B > 65535) return fail(ASR_EINVAL, "need 0 < B <= 65535 and n > 0");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    ASR_CUDA_TRY(cudaMemsetAsync(d_counts, 0, sizeof(unsigned long long) * 4 * B, st));
+    ASR_LAUNCH(k_iou_counts, dim3(16, B), 256, 0, st, d_true, d_pred, (size_t)n, class_id, include_bg, d_counts);
+    ASR_CUDA_TRY(cudaGetLastError());
+    return ASR_OK;
+}
 
 extern "C" int asr_warp_affine(const float* d_image, const float* h_angles, const float* h_shifts, int N, int H, int W,
                                int C, int interp, float* d_out, void* stream) {

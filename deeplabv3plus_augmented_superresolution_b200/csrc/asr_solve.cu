@@ -32,7 +32,11 @@ struct ImgParams {
     int optimizer, amsgrad, nesterov;
     int num_iter;
     int n_kept;
-    int pad0, pad1;
+    int use_btv;        // bilateral TV (superresolution.py:8-23) instead of tf.image.image_gradients TV
+    int pad0;
+    float btv_w[5];     // 0.6^n, n = |h|+|v|
+    float btv_lw[5];    // fl(lambda_tv * 0.6^n)
+    int pad1, pad2;
 };
 // per (iteration, image): x = learning rate of that step, y = optimizer-specific step scale
 // (Adam: lr*sqrt(1-b2^t)/(1-b1^t); Adamax: lr/(1-b1^t))
@@ -281,7 +285,7 @@ __device__ __forceinline__ float2 inv_translate_taps(int q, float u, int s, int 
     return ((int)f == q + s) ? make_float2(w0, w1) : make_float2(0.0f, w0);
 }
 
-template <bool WRITE_GRAD>
+template <bool WRITE_GRAD, bool BTV>
 __global__ void __launch_bounds__(K2_THREADS, 2)
 k_gradient_update(const float* __restrict__ x_cur, float* __restrict__ x_next, float* __restrict__ s0,
                   float* __restrict__ s1, float* __restrict__ s2, const float* __restrict__ resid,
@@ -455,10 +459,25 @@ k_gradient_update(const float* __restrict__ x_cur, float* __restrict__ x_next, f
             const size_t i = (size_t)Y * W + X;
             const float xi = xc[i];
             float g = acc[2 * r + c];
-            if (Y > 0) g = fadd(g, fmul(P.lambda_tv, sgn(fsub(xi, xc[i - W]))));
-            if (X > 0) g = fadd(g, fmul(P.lambda_tv, sgn(fsub(xi, xc[i - 1]))));
-            if (Y < H - 1) g = fsub(g, fmul(P.lambda_tv, sgn(fsub(xc[i + W], xi))));
-            if (X < W - 1) g = fsub(g, fmul(P.lambda_tv, sgn(fsub(xc[i + 1], xi))));
+            if (BTV && P.use_btv) {
+                // bilateral TV: 15 integer shifts (h in [-2,2], v in [0,2]) by nearest translate with zero fill;
+                // d/dx of w*|x - S(x)| is w*sign(d) here minus the same term pulled back by the inverse shift
+                for (int hh = -2; hh <= 2; ++hh) {
+                    for (int vv = 0; vv <= 2; ++vv) {
+                        const float lw = P.btv_lw[abs(hh) + vv];
+                        const int xs = X - hh, ys = Y - vv, xt = X + hh, yt = Y + vv;
+                        const float shifted = (xs >= 0 && xs < W && ys >= 0) ? xc[(size_t)ys * W + xs] : 0.0f;
+                        const float gd = fmul(lw, sgn(fsub(xi, shifted)));
+                        const float gb = (xt >= 0 && xt < W && yt < H) ? fmul(lw, sgn(fsub(xc[(size_t)yt * W + xt], xi))) : 0.0f;
+                        g = fadd(g, fsub(gd, gb));
+                    }
+                }
+            } else {
+                if (Y > 0) g = fadd(g, fmul(P.lambda_tv, sgn(fsub(xi, xc[i - W]))));
+                if (X > 0) g = fadd(g, fmul(P.lambda_tv, sgn(fsub(xi, xc[i - 1]))));
+                if (Y < H - 1) g = fsub(g, fmul(P.lambda_tv, sgn(fsub(xc[i + W], xi))));
+                if (X < W - 1) g = fsub(g, fmul(P.lambda_tv, sgn(fsub(xc[i + 1], xi))));
+            }
             g = fadd(g, fmul(P.lambda_l2, fmul(xi, 2.0f)));
             if (P.lambda_l1 > 0.0f) g = fadd(g, fmul(P.lambda_l1, sgn(xi)));
             const size_t gi = (size_t)b * plane + i;
@@ -529,8 +548,17 @@ __global__ void k_loss_terms(const float* __restrict__ xa, const float* __restri
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nx; i += (size_t)gridDim.x * blockDim.x) {
         const int Y = (int)(i / W), X = (int)(i % W);
         const float xi = x[i];
-        if (Y < H - 1) tv += fabs((double)fsub(x[i + W], xi));
-        if (X < W - 1) tv += fabs((double)fsub(x[i + 1], xi));
+        if (P.use_btv) {
+            for (int hh = -2; hh <= 2; ++hh)
+                for (int vv = 0; vv <= 2; ++vv) {
+                    const int xs = X - hh, ys = Y - vv;
+                    const float shifted = (xs >= 0 && xs < W && ys >= 0) ? x[(size_t)ys * W + xs] : 0.0f;
+                    tv += (double)P.btv_w[abs(hh) + vv] * fabs((double)fsub(xi, shifted));
+                }
+        } else {
+            if (Y < H - 1) tv += fabs((double)fsub(x[i + W], xi));
+            if (X < W - 1) tv += fabs((double)fsub(x[i + 1], xi));
+        }
         l2 += (double)xi * (double)xi;
         l1 += fabs((double)xi);
     }
@@ -607,7 +635,6 @@ static int check_shapes(int B, int N, int h, int w, int H, int W) {
 
 static int check_params(const AsrSolveParams* p, int n) {
     for (int i = 0; i < n; ++i) {
-        if (p[i].use_btv) return fail(ASR_EUNSUPPORTED, "use_BTV (bilateral TV, superresolution.py:8-23) is not implemented");
         if (p[i].optimizer < ASR_OPT_ADAM || p[i].optimizer > ASR_OPT_ADAMAX) return fail(ASR_EINVAL, "unknown optimizer %d", p[i].optimizer);
         if (p[i].num_iter < 0) return fail(ASR_EINVAL, "num_iter < 0");
     }
@@ -629,6 +656,7 @@ struct HostTables {
     std::vector<AsrSolveParams> hp;
     std::vector<Sched> sched;
     int max_iter = 0, max_kept = 0;
+    bool any_btv = false;
 };
 
 static void build_tables(const AsrSolveParams* params, int n_params, const float* angles, const float* shifts,
@@ -664,6 +692,12 @@ static void build_tables(const AsrSolveParams* params, int n_params, const float
         q.epsilon = p.epsilon; q.momentum = p.momentum;
         q.optimizer = p.optimizer; q.amsgrad = p.amsgrad; q.nesterov = p.nesterov;
         q.num_iter = p.num_iter; q.n_kept = kept;
+        q.use_btv = p.use_btv ? 1 : 0;
+        if (p.use_btv) T.any_btv = true;
+        for (int n = 0; n < 5; ++n) {
+            q.btv_w[n] = powf(0.6f, (float)n);
+            q.btv_lw[n] = p.lambda_tv * q.btv_w[n];
+        }
         T.ip[b] = q;
         if (p.num_iter > T.max_iter) T.max_iter = p.num_iter;
         if (kept > T.max_kept) T.max_kept = kept;
@@ -744,8 +778,10 @@ static int configure_kernels() {
     static bool done = false;   // attribute is per-function, idempotent; a benign race at worst repeats it
     if (done) return ASR_OK;
     ASR_CUDA_TRY(cudaFuncSetAttribute(k_forward_residual, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K1_SMEM));
-    ASR_CUDA_TRY(cudaFuncSetAttribute(k_gradient_update<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K2_SMEM));
-    ASR_CUDA_TRY(cudaFuncSetAttribute(k_gradient_update<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K2_SMEM));
+    ASR_CUDA_TRY(cudaFuncSetAttribute(k_gradient_update<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K2_SMEM));
+    ASR_CUDA_TRY(cudaFuncSetAttribute(k_gradient_update<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K2_SMEM));
+    ASR_CUDA_TRY(cudaFuncSetAttribute(k_gradient_update<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K2_SMEM));
+    ASR_CUDA_TRY(cudaFuncSetAttribute(k_gradient_update<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K2_SMEM));
     done = true;
     return ASR_OK;
 }
@@ -812,9 +848,14 @@ extern "C" int asr_solve_batched(const AsrSolveParams* params, int n_params, con
             ASR_LAUNCH_TIMED(0, k_forward_residual, dim3(t1, T.max_kept, nb), K1_THREADS, K1_SMEM, st,
                 (it & 1) ? map_b : map_a, d_copies + ro, D.resid + ro, D.fwd + (size_t)b0 * N, D.src + (size_t)b0 * N, D.ip + b0,
                 it, N, h, w, H, W, ntj, div_magic(ntj), b0);
-            ASR_LAUNCH_TIMED(1, (k_gradient_update<false>), dim3(t2, nb), K2_THREADS, K2_SMEM, st, 
-                xc, xn, D.s0 + po, D.s1 + po, D.s2 + po, D.resid + ro, D.inv + (size_t)b0 * N, D.ip + b0,
-                D.sched + b0, it, N, h, w, H, W, B);
+            if (T.any_btv)
+                ASR_LAUNCH_TIMED(1, (k_gradient_update<false, true>), dim3(t2, nb), K2_THREADS, K2_SMEM, st,
+                    xc, xn, D.s0 + po, D.s1 + po, D.s2 + po, D.resid + ro, D.inv + (size_t)b0 * N, D.ip + b0,
+                    D.sched + b0, it, N, h, w, H, W, B);
+            else
+                ASR_LAUNCH_TIMED(1, (k_gradient_update<false, false>), dim3(t2, nb), K2_THREADS, K2_SMEM, st,
+                    xc, xn, D.s0 + po, D.s1 + po, D.s2 + po, D.resid + ro, D.inv + (size_t)b0 * N, D.ip + b0,
+                    D.sched + b0, it, N, h, w, H, W, B);
         }
     }
     ASR_CUDA_TRY(cudaGetLastError());
@@ -855,8 +896,12 @@ extern "C" int asr_loss_grad_batched(const AsrSolveParams* params, int n_params,
     if (int e = make_x_map(&map_a, D.xa, B, H, W)) return e;
     ASR_LAUNCH_TIMED(0, k_forward_residual, dim3(t1, T.max_kept, B), K1_THREADS, K1_SMEM, st, map_a, d_copies, D.resid, D.fwd, D.src, D.ip,
                      0, N, h, w, H, W, ntj, div_magic(ntj), 0);
-    ASR_LAUNCH_TIMED(1, (k_gradient_update<true>), dim3(t2, B), K2_THREADS, K2_SMEM, st, D.xa, D.xb, D.s0, D.s1, D.s2, D.resid, D.inv, D.ip,
-                                                                      D.sched, 0, N, h, w, H, W, B);
+    if (T.any_btv)
+        ASR_LAUNCH_TIMED(1, (k_gradient_update<true, true>), dim3(t2, B), K2_THREADS, K2_SMEM, st, D.xa, D.xb, D.s0, D.s1, D.s2, D.resid,
+                         D.inv, D.ip, D.sched, 0, N, h, w, H, W, B);
+    else
+        ASR_LAUNCH_TIMED(1, (k_gradient_update<true, false>), dim3(t2, B), K2_THREADS, K2_SMEM, st, D.xa, D.xb, D.s0, D.s1, D.s2, D.resid,
+                         D.inv, D.ip, D.sched, 0, N, h, w, H, W, B);
     ASR_CUDA_TRY(cudaGetLastError());
     if (d_grad) ASR_CUDA_TRY(cudaMemcpyAsync(d_grad, D.xb, sizeof(float) * B * plane, cudaMemcpyDeviceToDevice, st));
     if (d_resid) {

@@ -94,3 +94,33 @@ def compute_IoU(true_image, image, img_size=(512, 512), class_id=None, include_b
     if class_id is not None:
         return single_class_IOU(true_image, image, class_id, include_bg)
     return Mean_IOU(true_image, image)
+
+
+def compute_IoU_batched(true_images, images, class_id, include_bg=False):
+    """compute_IoU (single-class branch) for B label images at once on the device.
+    true_images / images: CUDA int32 tensors [B,...] with the same number of pixels per image.
+    Returns a float64 ndarray [B]; NaN where every union is empty, as the reference's mean of nothing."""
+    from . import _lib
+    torch = _lib._torch()
+    L = _lib.lib()
+    t = true_images.to(device="cuda", dtype=torch.int32).contiguous()
+    p = images.to(device="cuda", dtype=torch.int32).contiguous()
+    B = t.shape[0]
+    n = t[0].numel()
+    assert p.shape[0] == B and p[0].numel() == n
+    counts = torch.empty((B, 4), dtype=torch.int64, device=t.device)
+    with torch.cuda.device(t.device):
+        _lib.check(L.asr_iou_counts(t.data_ptr(), p.data_ptr(), B, n, int(class_id), int(bool(include_bg)), counts.data_ptr(),
+                                    _lib._stream_ptr(torch)))
+    c = counts.cpu().numpy().astype(np.float64)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        iou_c = np.where(c[:, 1] > 0, c[:, 0] / c[:, 1], np.nan)
+        iou_b = np.where(c[:, 3] > 0, c[:, 2] / c[:, 3], np.nan)
+    if not include_bg:
+        return iou_c
+    stack = np.stack([iou_c, iou_b], 1)
+    out = np.full(B, np.nan)
+    ok = ~np.isnan(stack)
+    has = ok.any(1)
+    out[has] = np.nansum(stack[has], 1) / ok[has].sum(1)
+    return out

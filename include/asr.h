@@ -62,7 +62,7 @@ typedef struct AsrSolveParams {
     int32_t lr_scheduler;             /* ExponentialDecay on/off (optimizer.py:43-52) */
     float decay_steps, decay_rate;
     int64_t step_offset;
-    int32_t use_btv;                  /* superresolution.py:78 -- ASR_EUNSUPPORTED when non-zero */
+    int32_t use_btv;                  /* bilateral TV instead of TV (superresolution.py:8-23,78) */
     int32_t images_in_flight;         /* perf knob read from params[0]: images per launch group, 0 = all */
 } AsrSolveParams;
 
@@ -130,6 +130,13 @@ int asr_minmax_normalize(const float* d_in, int64_t n, float new_min, float new_
  * d_out int32 {0, th_value}.  d_workspace: 2*B floats.                                            */
 int asr_threshold(const float* d_x, int B, int64_t n, int32_t th_value, float th_factor,
                   const float* d_th_mask, int32_t* d_out, void* d_workspace, void* stream);
+
+/* ---- utils.py:180-204  single_class_IOU, the counting part ---------------------------------------
+ * B label images of n pixels (int32).  d_counts [B,4] = {inter, union} for class_id, then for class 0
+ * (ground truth relabelled to {class_id, 0} when include_bg).  The caller divides and drops empty
+ * unions (NaN) before averaging, as the reference does.                                           */
+int asr_iou_counts(const int32_t* d_true, const int32_t* d_pred, int B, int64_t n, int class_id, int include_bg,
+                   unsigned long long* d_counts, void* stream);
 
 /* ---- DLPack front door (north_star: "ctypes over DLPack buffers") ----------------------------
  * Same calls taking DLTensor* (dlpack.h v0.8 layout) for the device arrays; they validate

@@ -25,7 +25,7 @@ def declared_symbols():
 
 def test_exports_every_declared_symbol(L):
     names = declared_symbols()
-    assert len(names) == len(_lib.SIGNATURES) == 14
+    assert len(names) == len(_lib.SIGNATURES) == 15
     for n in names:
         assert hasattr(L, n), f"libasr.so does not export {n}"
         assert n in _lib.SIGNATURES, f"{n} has no ctypes signature"
@@ -56,8 +56,8 @@ def test_workspace_query_and_error_codes(L):
     assert L.asr_solve_batched(*args(p, 1, ws=16)) == -5                                     # workspace too small
     assert L.asr_solve_batched(*args(p, 2)) == -1                                           # n_params must be 1 or B
     assert L.asr_solve_batched(*args(p, 1, H=128)) == -3
-    pb = _lib.SolveParams(use_btv=True).to_c()
-    assert L.asr_solve_batched(*args(pb, 1)) == -3 and b"BTV" in L.asr_last_error()
+    pb = _lib.SolveParams(optimizer="adam").to_c(); pb.optimizer = 9
+    assert L.asr_solve_batched(*args(pb, 1)) == -1 and b"optimizer" in L.asr_last_error()
     assert L.asr_solve_batched(None, 1, fake, ang.ctypes.data_as(_lib._fp), shf.ctypes.data_as(_lib._fp), None,
                                1, 4, 16, 16, 64, 64, fake, None, fake, 1 << 30, None) == -2
     with pytest.raises(NotImplementedError):

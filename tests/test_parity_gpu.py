@@ -61,6 +61,8 @@ CASES = [
     dict(N=5, hw=(16, 16), iters=15, seed=6, kw=dict(optimizer="adadelta", learning_rate=1.0)),
     dict(N=5, hw=(16, 16), iters=15, seed=6, kw=dict(optimizer="adamax", learning_rate=2e-3, step_offset=45)),
     dict(N=4, hw=(16, 16), iters=6, seed=8, kw=dict(lambda_df=0.37, lambda_tv=0.11, lambda_l2=0.0, decay_steps=3, decay_rate=0.5)),
+    dict(N=5, hw=(32, 32), iters=12, seed=12, kw=dict(use_btv=True)),                                       # bilateral TV
+    dict(N=4, hw=(16, 24), iters=9, seed=13, value=8.0, kw=dict(use_btv=True, lambda_tv=0.05, lambda_l1=0.01, amsgrad=False)),
 ]
 
 
@@ -236,6 +238,20 @@ def test_backproject(mode):
     one, none = fn([c[..., None] for c in copies[0].cpu().numpy()], ang[0], sh[0])
     assert none is None and one.shape == (128, 128, 1) and one.dtype == np.float32
     np.testing.assert_array_equal(one[..., 0], out[0].cpu().numpy())
+
+
+def test_iou_counts_on_device():
+    from deeplabv3plus_augmented_superresolution_b200 import utils
+    rng = np.random.RandomState(8)
+    t = rng.choice([0, 8, 15, 255], size=(5, 64, 64, 1), p=[0.6, 0.25, 0.1, 0.05]).astype(np.int32)
+    p = np.where(rng.rand(5, 64, 64, 1) < 0.8, np.where(t == 8, 8, 0), rng.choice([0, 8], size=t.shape)).astype(np.int32)
+    t[3] = 0; p[3] = 0                      # class absent everywhere: NaN without bg, 1.0 with bg
+    for bg in (False, True):
+        got = utils.compute_IoU_batched(torch.from_numpy(t).cuda(), torch.from_numpy(p).cuda(), 8, include_bg=bg)
+        for b in range(5):
+            ref = utils.compute_IoU(t[b], p[b], img_size=(64, 64), class_id=8, include_bg=bg)
+            orc = O.compute_iou(t[b], p[b], 8, include_bg=bg)
+            assert (np.isnan(ref) and np.isnan(got[b]) and np.isnan(orc)) or (got[b] == ref and abs(orc - ref) < 1e-15)
 
 
 # --------------------------------------------------------------------------------------------------
