@@ -28,6 +28,9 @@ __device__ __forceinline__ float dec(unsigned e) {
 // the integer window (Z+s, Z+s+1), s = floor(-d), so the CTA first evaluates p once per position of
 // the 33x33 window into shared memory (each p would otherwise be recomputed by its 4 consumers),
 // then forms the outputs with per-column/row tap tables carrying the literal translate weights.
+// The source image is first padded to 4 channels so that every tap is one 128-bit load, p lives in
+// shared memory as float4, and the finished tile is staged in shared memory and written with
+// row-contiguous 128-bit stores (a 32-pixel RGB row segment is 384 contiguous bytes).
 constexpr int K3_T = 32;
 constexpr int K3_P = K3_T + 1;
 constexpr int K3_THREADS = 256;
@@ -53,10 +56,24 @@ __device__ __forceinline__ float2 warp_taps(int Z, float t, int s, int limit, in
     return make_float2(wa, wb);
 }
 
+__global__ void k_pad_channels(const float* __restrict__ img, float4* __restrict__ out, size_t npx, int C) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < npx; i += (size_t)gridDim.x * blockDim.x) {
+        float v[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int c = 0; c < C; ++c) v[c] = img[i * C + c];
+        out[i] = make_float4(v[0], v[1], v[2], v[3]);
+    }
+}
+
+__device__ __forceinline__ float4 bilerp4(float4 a, float4 b, float4 c, float4 d, float wx0, float wx1, float wy0, float wy1) {
+    return make_float4(bilerp(a.x, b.x, c.x, d.x, wx0, wx1, wy0, wy1), bilerp(a.y, b.y, c.y, d.y, wx0, wx1, wy0, wy1),
+                       bilerp(a.z, b.z, c.z, d.z, wx0, wx1, wy0, wy1), bilerp(a.w, b.w, c.w, d.w, wx0, wx1, wy0, wy1));
+}
+
+template <int C>
 __global__ void __launch_bounds__(K3_THREADS)
-k_warp_affine(const float* __restrict__ img, const WarpXf* __restrict__ xf, float* __restrict__ out, int H, int W, int C,
-              int interp) {
-    __shared__ float p[K3_P * K3_P * K3_CMAX];
+k_warp_affine(const float4* __restrict__ img, const WarpXf* __restrict__ xf, float* __restrict__ out, int H, int W, int interp) {
+    __shared__ float4 p[K3_P * K3_P];
+    __shared__ __align__(16) float outs[K3_T * K3_T * C];
     __shared__ float2 colw[K3_T], roww[K3_T];
     const int k = blockIdx.y, tid = threadIdx.x;
     const int ntx = (W + K3_T - 1) / K3_T;
@@ -64,15 +81,17 @@ k_warp_affine(const float* __restrict__ img, const WarpXf* __restrict__ xf, floa
     const WarpXf T = xf[k];
     const int sx = (int)floorf(T.tx), sy = (int)floorf(T.ty);
     const int qx_lo = X0 + sx, qy_lo = Y0 + sy;
+    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
 
     if (tid < K3_T) colw[tid] = warp_taps(X0 + tid, T.tx, sx, W, interp);
     else if (tid < 2 * K3_T) roww[tid - K3_T] = warp_taps(Y0 + tid - K3_T, T.ty, sy, H, interp);
 
+    // ---- rotated image on the (T+1)^2 window ---------------------------------------------------------
     for (int e = tid; e < K3_P * K3_P; e += K3_THREADS) {
-        const int py = e / K3_P, px = e % K3_P;
+        const int py = e / K3_P, px = e - py * K3_P;
         const float qx = (float)(qx_lo + px), qy = (float)(qy_lo + py);
         const float ix = affine_coord(T.r0, qx, T.r1, qy, T.r2), iy = affine_coord(T.r3, qx, T.r4, qy, T.r5);
-        float* dst = p + e * C;
+        float4 v;
         if (interp == ASR_INTERP_BILINEAR) {
             const float fx = floorf(ix), fy = floorf(iy);
             const float wx0 = fsub(fadd(fx, 1.0f), ix), wx1 = fsub(ix, fx);
@@ -80,39 +99,57 @@ k_warp_affine(const float* __restrict__ img, const WarpXf* __restrict__ xf, floa
             const int x0 = (int)fx, y0 = (int)fy;
             const bool vx0 = x0 >= 0 && x0 < W, vx1 = x0 + 1 >= 0 && x0 + 1 < W;
             const bool vy0 = y0 >= 0 && y0 < H, vy1 = y0 + 1 >= 0 && y0 + 1 < H;
-            const float* b00 = img + ((size_t)y0 * W + x0) * C;
-            for (int c = 0; c < C; ++c) {
-                const float v00 = (vy0 && vx0) ? __ldg(b00 + c) : 0.0f;
-                const float v01 = (vy0 && vx1) ? __ldg(b00 + C + c) : 0.0f;
-                const float v10 = (vy1 && vx0) ? __ldg(b00 + (size_t)W * C + c) : 0.0f;
-                const float v11 = (vy1 && vx1) ? __ldg(b00 + (size_t)W * C + C + c) : 0.0f;
-                dst[c] = bilerp(v00, v01, v10, v11, wx0, wx1, wy0, wy1);
-            }
+            const float4* b00 = img + ((ptrdiff_t)y0 * W + x0);
+            const float4 v00 = (vy0 && vx0) ? __ldg(b00) : zero4;
+            const float4 v01 = (vy0 && vx1) ? __ldg(b00 + 1) : zero4;
+            const float4 v10 = (vy1 && vx0) ? __ldg(b00 + W) : zero4;
+            const float4 v11 = (vy1 && vx1) ? __ldg(b00 + W + 1) : zero4;
+            v = bilerp4(v00, v01, v10, v11, wx0, wx1, wy0, wy1);
         } else {
             const long xn = (long)roundf(ix), yn = (long)roundf(iy);
-            const bool v = xn >= 0 && xn < W && yn >= 0 && yn < H;
-            for (int c = 0; c < C; ++c) dst[c] = v ? __ldg(img + ((size_t)yn * W + xn) * C + c) : 0.0f;
+            v = (xn >= 0 && xn < W && yn >= 0 && yn < H) ? __ldg(img + ((size_t)yn * W + xn)) : zero4;
         }
+        p[e] = v;
     }
     __syncthreads();
 
-    float* ok = out + (size_t)k * H * W * C;
-    const int row_elems = K3_T * C;
-    for (int e = tid; e < K3_T * row_elems; e += K3_THREADS) {
-        const int ty = e / row_elems, rem = e % row_elems, tx = rem / C, c = rem % C;
-        const int X = X0 + tx, Y = Y0 + ty;
-        if (X >= W || Y >= H) continue;
+    // ---- translate stage: 4 output pixels per thread into the staging tile -----------------------------
+#pragma unroll
+    for (int j = 0; j < K3_T * K3_T / K3_THREADS; ++j) {
+        const int ty = (tid >> 5) + 8 * j, tx = tid & 31;
         const float2 wc = colw[tx], wr = roww[ty];
-        const float* p00 = p + (ty * K3_P + tx) * C + c;
-        float v;
+        const float4 a = p[ty * K3_P + tx], b = p[ty * K3_P + tx + 1], c = p[(ty + 1) * K3_P + tx], d = p[(ty + 1) * K3_P + tx + 1];
+        float4 v;
         if (interp == ASR_INTERP_BILINEAR) {
-            v = bilerp(p00[0], p00[C], p00[K3_P * C], p00[K3_P * C + C], wc.x, wc.y, wr.x, wr.y);
+            v = bilerp4(a, b, c, d, wc.x, wc.y, wr.x, wr.y);
         } else {   // exactly one tap has weight 1 (or none: zero fill)
-            const float a = (wc.x != 0.0f) ? p00[0] : ((wc.y != 0.0f) ? p00[C] : 0.0f);
-            const float bq = (wc.x != 0.0f) ? p00[K3_P * C] : ((wc.y != 0.0f) ? p00[K3_P * C + C] : 0.0f);
-            v = (wr.x != 0.0f) ? a : ((wr.y != 0.0f) ? bq : 0.0f);
+            const float4 top = (wc.x != 0.0f) ? a : ((wc.y != 0.0f) ? b : zero4);
+            const float4 bot = (wc.x != 0.0f) ? c : ((wc.y != 0.0f) ? d : zero4);
+            v = (wr.x != 0.0f) ? top : ((wr.y != 0.0f) ? bot : zero4);
         }
-        ok[((size_t)Y * W + X) * C + c] = v;
+        float* o = outs + (ty * K3_T + tx) * C;
+        o[0] = v.x;
+        if (C > 1) o[1] = v.y;
+        if (C > 2) o[2] = v.z;
+        if (C > 3) o[3] = v.w;
+    }
+    __syncthreads();
+
+    // ---- write the tile: each row segment is K3_T*C contiguous floats ------------------------------------
+    float* ok = out + (size_t)k * H * W * C;
+    const bool full = (X0 + K3_T <= W) && (Y0 + K3_T <= H) && (((size_t)W * C) % 4 == 0) && ((X0 * C) % 4 == 0) && ((K3_T * C) % 4 == 0);
+    if (full) {
+        constexpr int ROW4 = K3_T * C / 4;
+        for (int e = tid; e < K3_T * ROW4; e += K3_THREADS) {
+            const int ty = e / ROW4, c4 = e - ty * ROW4;
+            const float4 v = *reinterpret_cast<const float4*>(outs + ty * K3_T * C + 4 * c4);
+            *reinterpret_cast<float4*>(ok + ((size_t)(Y0 + ty) * W + X0) * C + 4 * c4) = v;
+        }
+    } else {
+        for (int e = tid; e < K3_T * K3_T * C; e += K3_THREADS) {
+            const int ty = e / (K3_T * C), rem = e - ty * (K3_T * C), tx = rem / C;
+            if (X0 + tx < W && Y0 + ty < H) ok[((size_t)(Y0 + ty) * W + X0) * C + rem] = outs[e];
+        }
     }
 }
 
@@ -341,13 +378,24 @@ extern "C" int asr_warp_affine(const float* d_image, const float* h_angles, cons
         rotate_matrix(h_angles[k], H, W, r);
         xf[k] = WarpXf{r[0], r[1], r[2], r[3], r[4], r[5], -h_shifts[2 * k], -h_shifts[2 * k + 1]};
     }
-    WarpXf* d_xf = nullptr;
-    ASR_CUDA_TRY(cudaMallocAsync((void**)&d_xf, sizeof(WarpXf) * N, st));   // transient table, freed in stream order
+    // transient, stream-ordered scratch: the per-copy table and the image padded to 4 channels
+    const size_t npx = (size_t)H * W;
+    unsigned char* scratch = nullptr;
+    const size_t xf_bytes = (sizeof(WarpXf) * N + 255) / 256 * 256;
+    ASR_CUDA_TRY(cudaMallocAsync((void**)&scratch, xf_bytes + sizeof(float4) * npx, st));
+    WarpXf* d_xf = reinterpret_cast<WarpXf*>(scratch);
+    float4* d_pad = reinterpret_cast<float4*>(scratch + xf_bytes);
     ASR_CUDA_TRY(cudaMemcpyAsync(d_xf, xf.data(), sizeof(WarpXf) * N, cudaMemcpyHostToDevice, st));
+    ASR_LAUNCH(k_pad_channels, 296, 256, 0, st, d_image, d_pad, npx, C);
     const int tiles = ((W + K3_T - 1) / K3_T) * ((H + K3_T - 1) / K3_T);
-    ASR_LAUNCH(k_warp_affine, dim3(tiles, N), K3_THREADS, 0, st, d_image, d_xf, d_out, H, W, C, interp);
+    switch (C) {
+    case 1: ASR_LAUNCH(k_warp_affine<1>, dim3(tiles, N), K3_THREADS, 0, st, d_pad, d_xf, d_out, H, W, interp); break;
+    case 2: ASR_LAUNCH(k_warp_affine<2>, dim3(tiles, N), K3_THREADS, 0, st, d_pad, d_xf, d_out, H, W, interp); break;
+    case 3: ASR_LAUNCH(k_warp_affine<3>, dim3(tiles, N), K3_THREADS, 0, st, d_pad, d_xf, d_out, H, W, interp); break;
+    default: ASR_LAUNCH(k_warp_affine<4>, dim3(tiles, N), K3_THREADS, 0, st, d_pad, d_xf, d_out, H, W, interp); break;
+    }
     ASR_CUDA_TRY(cudaGetLastError());
-    ASR_CUDA_TRY(cudaFreeAsync(d_xf, st));
+    ASR_CUDA_TRY(cudaFreeAsync(scratch, st));
     return ASR_OK;
 }
 

@@ -79,14 +79,19 @@ __global__ void k_init_upsample(const float* __restrict__ copies, float* __restr
 // op's fill), evaluates the 48x48 needed p values with the op's arithmetic, and a second phase
 // combines them per cell with per-column/row tap tables that carry the literal translate weights,
 // the zero fill of p outside the canvas, and the rounding case floor(fl(Z-dx)) == Z+floor(-dx)+1.
-constexpr int K1_T = 16;               // LR tile edge (cells)
-constexpr int K1_THREADS = 192;        // 48 p-columns x 4 row groups
-constexpr int K1_P = 3 * K1_T;         // p positions per tile edge
-constexpr int K1_PBS = K1_P + 1;       // p buffer stride
-constexpr int K1_XS = 96;              // TMA box width  (floats): 62*sqrt(2)+3 < 96, multiple of 32 -> conflict-free gathers
-constexpr int K1_XR = 92;              // TMA box height
-constexpr unsigned K1_BOX_BYTES = K1_XS * K1_XR * sizeof(float);
-constexpr size_t K1_SMEM = K1_BOX_BYTES + sizeof(float) * (K1_P * K1_PBS) + sizeof(float4) * 2 * K1_T;
+constexpr int K1_TJ = 16;              // LR tile: 16 cells wide ...
+constexpr int K1_TI = 12;              // ... 12 cells tall = 192 cells, one per thread in the second phase
+constexpr int K1_THREADS = 192;        // 48 p-columns x 4 row groups of 9 rows
+constexpr int K1_PC = 3 * K1_TJ;       // needed p columns (48) and rows (36) per tile
+constexpr int K1_PR = 3 * K1_TI;
+constexpr int K1_PBS = K1_PC + 1;      // p buffer stride
+constexpr int K1_XS = 96;              // TMA box width  (floats): 62*sqrt(2)+2+3 < 96, multiple of 32 -> conflict-free gathers
+constexpr int K1_XR_SMALL = 68;        // TMA box height when 62|sin|+46|cos|+3 <= 68 for every copy (|angle| <~ 0.36 rad): 6 CTAs/SM
+constexpr int K1_XR_BIG = 84;          // ... for any rotation: sqrt(62^2+46^2)+3 < 84: 5 CTAs/SM
+template <int XR>
+constexpr size_t k1_smem() {
+    return sizeof(float) * K1_XS * XR + sizeof(float) * (K1_PR * K1_PBS) + sizeof(float4) * (K1_TJ + K1_TI) + 16;
+}
 
 // translate stencil weights of z-column Z on the window (Z+s, Z+s+1), validity of p folded in
 __device__ __forceinline__ float2 translate_taps(int Z, float t, int s, int limit) {
@@ -127,6 +132,7 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, i
                  : "memory");
 }
 
+template <int XR>
 __global__ void __launch_bounds__(K1_THREADS)
 k_forward_residual(const __grid_constant__ CUtensorMap xmap, const float* __restrict__ copies, float* __restrict__ resid,
                    const FwdXf* __restrict__ fwd, const int* __restrict__ src_idx,
@@ -138,66 +144,65 @@ k_forward_residual(const __grid_constant__ CUtensorMap xmap, const float* __rest
 
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ __align__(8) unsigned long long bar;
-    float* xt = reinterpret_cast<float*>(smem_raw);                              // [K1_XR][K1_XS], filled by TMA
-    float* pb = xt + K1_XS * K1_XR;                                              // [K1_P][K1_PBS]
-    float4* colw = reinterpret_cast<float4*>(pb + K1_P * K1_PBS);                // [K1_T] (w1a,w1b,w2a,w2b)
-    float4* roww = colw + K1_T;
+    float* xt = reinterpret_cast<float*>(smem_raw);                              // [XR][K1_XS], filled by TMA
+    float* pb = xt + K1_XS * XR;                                                 // [K1_PR][K1_PBS]
+    float4* colw = reinterpret_cast<float4*>(pb + K1_PR * K1_PBS);               // [K1_TJ] (w1a,w1b,w2a,w2b)
+    float4* roww = colw + K1_TJ;                                                 // [K1_TI]
+    int* boxs = reinterpret_cast<int*>(roww + K1_TI);                            // bx0a, by0, empty
 
     const int tid = threadIdx.x, lane = tid & 31;
-    const int ti = (int)__umulhi(blockIdx.x, ntj_magic), tj = (int)blockIdx.x - ti * ntj;   // tile row / column
-    const int j0 = tj * K1_T, i0 = ti * K1_T;
+    const int ti = (ntj == 1) ? (int)blockIdx.x : (int)__umulhi(blockIdx.x, ntj_magic);          // tile row (2^32/1 does not fit the magic)
+    const int tj = (int)blockIdx.x - ti * ntj;                                                    // tile column
+    const int j0 = tj * K1_TJ, i0 = ti * K1_TI;
     const FwdXf T = fwd[(size_t)b * N + ks];
     const int sx = (int)floorf(T.tx), sy = (int)floorf(T.ty);
     const int qx_lo = 4 * j0 + 1 + sx, qy_lo = 4 * i0 + 1 + sy;   // first needed p position
-    constexpr int SPAN = 4 * (K1_T - 1) + 2;                      // last needed = lo + SPAN
+    constexpr int SPAN_X = 4 * (K1_TJ - 1) + 2, SPAN_Y = 4 * (K1_TI - 1) + 2;   // last needed = lo + SPAN
 
-    if (tid == 0) mbar_init(&bar, 1);
-
-    // ---- source bounding box of the p region: each rounded op of the coordinate is monotone in qx
-    //      and in qy, so the literal coordinates of the four corners bound every tap -----------------
-    float cix, ciy;
-    {
-        const float qx = (float)(qx_lo + ((lane & 1) ? SPAN : 0)), qy = (float)(qy_lo + ((lane & 2) ? SPAN : 0));
-        cix = affine_coord(T.r0, qx, T.r1, qy, T.r2);
-        ciy = affine_coord(T.r3, qx, T.r4, qy, T.r5);
-    }
-    const int bx0 = (int)floorf(warp_min(cix)), bx1 = (int)floorf(warp_max(cix)) + 1;
-    const int by0 = (int)floorf(warp_min(ciy)), by1 = (int)floorf(warp_max(ciy)) + 1;
-    // TMA needs the innermost start coordinate 16-byte aligned (an unaligned start faults with
-    // "illegal instruction" on B200: scripts/dev/tma_test3.cu), so the box starts at bx0 rounded down to 4
-    const int bx0a = bx0 & ~3;
-    if (bx1 - bx0a >= K1_XS || by1 - by0 >= K1_XR) return;  // cannot happen for a rotation (box <= 62*sqrt(2)+2+3)
-    const bool empty = (bx1 < 0 || bx0 >= W || by1 < 0 || by0 >= H);  // rotated image is all zero here
-
-    __syncthreads();                                               // barrier init visible
-    if (tid == 0 && !empty) tma_load_3d(xt, &xmap, bx0a, by0, b_base + b, &bar, K1_BOX_BYTES);
-
-    // ---- tap tables, overlapped with the TMA flight (read after the next __syncthreads) ---------
-    if (tid >= 64 && tid < 64 + K1_T) {
+    if (tid < 32) {
+        // ---- warp 0: source bounding box of the p region.  Each rounded op of the coordinate is monotone
+        //      in qx and in qy, so the literal coordinates of the four corners bound every tap. -------------
+        const float qx = (float)(qx_lo + ((lane & 1) ? SPAN_X : 0)), qy = (float)(qy_lo + ((lane & 2) ? SPAN_Y : 0));
+        const float cix = affine_coord(T.r0, qx, T.r1, qy, T.r2), ciy = affine_coord(T.r3, qx, T.r4, qy, T.r5);
+        const int bx0 = (int)floorf(warp_min(cix)), bx1 = (int)floorf(warp_max(cix)) + 1;
+        const int by0 = (int)floorf(warp_min(ciy)), by1 = (int)floorf(warp_max(ciy)) + 1;
+        // TMA needs the innermost start coordinate 16-byte aligned (an unaligned start faults with
+        // "illegal instruction" on B200: scripts/dev/tma_test3.cu), so the box starts at bx0 rounded down to 4
+        const int bx0a = bx0 & ~3;
+        // empty: the rotated image is all zero here (a box beyond the buffer cannot happen for a rotation)
+        const int empty = (bx1 < 0 || bx0 >= W || by1 < 0 || by0 >= H || bx1 - bx0a >= K1_XS || by1 - by0 >= XR);
+        if (lane == 0) {
+            boxs[0] = bx0a; boxs[1] = by0; boxs[2] = empty;
+            mbar_init(&bar, 1);
+            if (!empty) tma_load_3d(xt, &xmap, bx0a, by0, b_base + b, &bar, (unsigned)(K1_XS * XR * sizeof(float)));
+        }
+    } else if (tid >= 64 && tid < 64 + K1_TJ) {
+        // ---- tap tables, overlapped with the TMA flight -------------------------------------------------------
         const int c = tid - 64, Z1 = 4 * (j0 + c) + 1;
         const float2 a = translate_taps(Z1, T.tx, sx, W), d = translate_taps(Z1 + 1, T.tx, sx, W);
         colw[c] = make_float4(a.x, a.y, d.x, d.y);
-    } else if (tid >= 96 && tid < 96 + K1_T) {
+    } else if (tid >= 96 && tid < 96 + K1_TI) {
         const int c = tid - 96, Z1 = 4 * (i0 + c) + 1;
         const float2 a = translate_taps(Z1, T.ty, sy, H), d = translate_taps(Z1 + 1, T.ty, sy, H);
         roww[c] = make_float4(a.x, a.y, d.x, d.y);
     }
+    __syncthreads();   // box, barrier init and tables visible
+    const bool empty = boxs[2] != 0;
 
     if (!empty) {
         // ---- p = rotate-gather of x at the needed integer positions ------------------------------
-        const int pcn = tid % K1_P, g = tid / K1_P;               // p column, row group (12 rows each)
-        const int qx = qx_lo + 4 * (pcn / 3) + (pcn % 3);
-        const float qxf = (float)qx;
+        const int pcn = tid % K1_PC, g = tid / K1_PC;             // p column, row group (9 rows = 3 cell rows each)
+        const float qxf = (float)(qx_lo + 4 * (pcn / 3) + (pcn % 3));
         const float ax = fmul(T.r0, qxf), ay = fmul(T.r3, qxf);
-        const float qyf0 = (float)(qy_lo + 16 * g);
+        const float qyf0 = (float)(qy_lo + 12 * g);
         // word offset of tap (y0,x0) = raw_y*XS + raw_x + cst (mod 2^32); kept opaque so that the compiler
         // cannot split the magic constant out of it and re-add it once per tap
-        unsigned cst = 0u - (unsigned)(kMagicBits + by0) * K1_XS - (unsigned)(kMagicBits + bx0a);
+        unsigned cst = 0u - (unsigned)(kMagicBits + boxs[1]) * K1_XS - (unsigned)(kMagicBits + boxs[0]);
         asm volatile("" : "+r"(cst));
-        float* prow = pb + (12 * g) * K1_PBS + pcn;
+        float* prow = pb + (9 * g) * K1_PBS + pcn;
         mbar_wait(&bar, 0);
 #pragma unroll
-        for (int m = 0; m < 12; ++m) {
+        for (int m = 0; m < 9; ++m) {
             const float qyf = qyf0 + (float)(4 * (m / 3) + (m % 3));   // exact small-integer add
             const float ix = fadd(fadd(ax, fmul(T.r1, qyf)), T.r2);
             const float iy = fadd(fadd(ay, fmul(T.r4, qyf)), T.r5);
@@ -212,14 +217,10 @@ k_forward_residual(const __grid_constant__ CUtensorMap xmap, const float* __rest
     }
     __syncthreads();
 
-    // ---- per cell: translate (2x2 z values), resize (literal lerps at 0.5), minus y --------------
-    const int src = src_idx[(size_t)b * N + ks];
-    const float* yk = copies + ((size_t)b * N + src) * h * w;
-    float* rk = resid + ((size_t)b * N + ks) * h * w;
-    for (int cell = tid; cell < K1_T * K1_T; cell += K1_THREADS) {
-        const int ci = cell / K1_T, cj = cell % K1_T;
-        const int i = i0 + ci, j = j0 + cj;
-        if (i >= h || j >= w) continue;
+    // ---- one cell per thread: translate (2x2 z values), resize (literal lerps at 0.5), minus y ---------
+    const int ci = tid / K1_TJ, cj = tid % K1_TJ;
+    const int i = i0 + ci, j = j0 + cj;
+    if (i < h && j < w) {
         float D = 0.0f;
         if (!empty) {
             const float4 wc = colw[cj], wr = roww[ci];
@@ -239,7 +240,8 @@ k_forward_residual(const __grid_constant__ CUtensorMap xmap, const float* __rest
             const float bot = fadd(bl, fmul(fsub(br, bl), 0.5f));
             D = fadd(top, fmul(fsub(bot, top), 0.5f));
         }
-        rk[i * w + j] = fsub(D, __ldg(yk + i * w + j));
+        const int src = src_idx[(size_t)b * N + ks];
+        resid[(((size_t)b * N + ks) * h + i) * w + j] = fsub(D, __ldg(copies + (((size_t)b * N + src) * h + i) * w + j));
     }
 }
 
@@ -657,6 +659,7 @@ struct HostTables {
     std::vector<Sched> sched;
     int max_iter = 0, max_kept = 0;
     bool any_btv = false;
+    bool small_box = true;   // every copy's K1 source box fits K1_XR_SMALL rows
 };
 
 static void build_tables(const AsrSolveParams* params, int n_params, const float* angles, const float* shifts,
@@ -681,6 +684,8 @@ static void build_tables(const AsrSolveParams* params, int n_params, const float
             invert_transform(tr, tri);
             const size_t o = (size_t)b * N + kept;
             T.fwd[o] = FwdXf{rot[0], rot[1], rot[2], rot[3], rot[4], rot[5], tr[2], tr[5]};
+            // K1 box rows <= 62|t3| + 46|t4| + 3 (corner span of the 63x47 p region, the +1 tap, floor); small margin
+            if (62.0f * fabsf(rot[3]) + 46.0f * fabsf(rot[4]) + 3.05f > (float)K1_XR_SMALL) T.small_box = false;
             T.inv[o] = InvXf{roti[0], roti[1], roti[2], roti[3], roti[4], roti[5], tri[2], tri[5]};
             T.src[o] = k;
             ++kept;
@@ -749,7 +754,7 @@ static int upload(const HostTables& T, const Device& D, cudaStream_t st) {
 }
 
 // 3-D tiled tensor map over an x buffer [B][H][W] fp32 with the K1 box; out-of-bounds elements read as zero
-static int make_x_map(CUtensorMap* map, const float* base, int B, int H, int W) {
+static int make_x_map(CUtensorMap* map, const float* base, int B, int H, int W, int box_rows) {
     typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -763,7 +768,7 @@ static int make_x_map(CUtensorMap* map, const float* base, int B, int H, int W) 
     }
     const cuuint64_t gdim[3] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
     const cuuint64_t gstride[2] = {(cuuint64_t)W * sizeof(float), (cuuint64_t)W * H * sizeof(float)};
-    const cuuint32_t box[3] = {K1_XS, K1_XR, 1};
+    const cuuint32_t box[3] = {K1_XS, (cuuint32_t)box_rows, 1};
     const cuuint32_t estr[3] = {1, 1, 1};
     const CUresult r = encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), gdim, gstride, box, estr,
                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -777,7 +782,8 @@ static unsigned div_magic(int d) { return (unsigned)((0x100000000ull + (unsigned
 static int configure_kernels() {
     static bool done = false;   // attribute is per-function, idempotent; a benign race at worst repeats it
     if (done) return ASR_OK;
-    ASR_CUDA_TRY(cudaFuncSetAttribute(k_forward_residual, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K1_SMEM));
+    ASR_CUDA_TRY(cudaFuncSetAttribute(k_forward_residual<K1_XR_SMALL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k1_smem<K1_XR_SMALL>()));
+    ASR_CUDA_TRY(cudaFuncSetAttribute(k_forward_residual<K1_XR_BIG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k1_smem<K1_XR_BIG>()));
     ASR_CUDA_TRY(cudaFuncSetAttribute(k_gradient_update<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K2_SMEM));
     ASR_CUDA_TRY(cudaFuncSetAttribute(k_gradient_update<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K2_SMEM));
     ASR_CUDA_TRY(cudaFuncSetAttribute(k_gradient_update<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K2_SMEM));
@@ -830,12 +836,13 @@ extern "C" int asr_solve_batched(const AsrSolveParams* params, int n_params, con
             ASR_LAUNCH(k_fill, 64, 256, 0, st, D.s0 + (size_t)b * plane, T.hp[b].initial_accumulator_value, plane);
     ASR_LAUNCH(k_init_upsample, dim3((W + 31) / 32, (H + 7) / 8, B), dim3(32, 8), 0, st, d_copies, D.xa, N, h, w, H, W);
 
-    const int ntj = (w + K1_T - 1) / K1_T;
-    const int t1 = ntj * ((h + K1_T - 1) / K1_T);
+    const int ntj = (w + K1_TJ - 1) / K1_TJ;
+    const int t1 = ntj * ((h + K1_TI - 1) / K1_TI);
     const int t2 = ((W + K2_T - 1) / K2_T) * ((H + K2_T - 1) / K2_T);
     CUtensorMap map_a, map_b;
-    if (int e = make_x_map(&map_a, D.xa, B, H, W)) return e;
-    if (int e = make_x_map(&map_b, D.xb, B, H, W)) return e;
+    const int box_rows = T.small_box ? K1_XR_SMALL : K1_XR_BIG;
+    if (int e = make_x_map(&map_a, D.xa, B, H, W, box_rows)) return e;
+    if (int e = make_x_map(&map_b, D.xb, B, H, W, box_rows)) return e;
     int group = params[0].images_in_flight > 0 ? params[0].images_in_flight : B;
     for (int b0 = 0; b0 < B; b0 += group) {
         const int nb = (B - b0 < group) ? B - b0 : group;
@@ -845,9 +852,14 @@ extern "C" int asr_solve_batched(const AsrSolveParams* params, int n_params, con
         for (int it = 0; it < iters; ++it) {
             float* xc = ((it & 1) ? D.xb : D.xa) + po;
             float* xn = ((it & 1) ? D.xa : D.xb) + po;
-            ASR_LAUNCH_TIMED(0, k_forward_residual, dim3(t1, T.max_kept, nb), K1_THREADS, K1_SMEM, st,
-                (it & 1) ? map_b : map_a, d_copies + ro, D.resid + ro, D.fwd + (size_t)b0 * N, D.src + (size_t)b0 * N, D.ip + b0,
-                it, N, h, w, H, W, ntj, div_magic(ntj), b0);
+            if (T.small_box)
+                ASR_LAUNCH_TIMED(0, k_forward_residual<K1_XR_SMALL>, dim3(t1, T.max_kept, nb), K1_THREADS, k1_smem<K1_XR_SMALL>(), st,
+                    (it & 1) ? map_b : map_a, d_copies + ro, D.resid + ro, D.fwd + (size_t)b0 * N, D.src + (size_t)b0 * N, D.ip + b0,
+                    it, N, h, w, H, W, ntj, div_magic(ntj), b0);
+            else
+                ASR_LAUNCH_TIMED(0, k_forward_residual<K1_XR_BIG>, dim3(t1, T.max_kept, nb), K1_THREADS, k1_smem<K1_XR_BIG>(), st,
+                    (it & 1) ? map_b : map_a, d_copies + ro, D.resid + ro, D.fwd + (size_t)b0 * N, D.src + (size_t)b0 * N, D.ip + b0,
+                    it, N, h, w, H, W, ntj, div_magic(ntj), b0);
             if (T.any_btv)
                 ASR_LAUNCH_TIMED(1, (k_gradient_update<false, true>), dim3(t2, nb), K2_THREADS, K2_SMEM, st,
                     xc, xn, D.s0 + po, D.s1 + po, D.s2 + po, D.resid + ro, D.inv + (size_t)b0 * N, D.ip + b0,
@@ -889,13 +901,17 @@ extern "C" int asr_loss_grad_batched(const AsrSolveParams* params, int n_params,
 
     const size_t plane = (size_t)H * W;
     ASR_CUDA_TRY(cudaMemcpyAsync(D.xa, d_x, sizeof(float) * B * plane, cudaMemcpyDeviceToDevice, st));
-    const int ntj = (w + K1_T - 1) / K1_T;
-    const int t1 = ntj * ((h + K1_T - 1) / K1_T);
+    const int ntj = (w + K1_TJ - 1) / K1_TJ;
+    const int t1 = ntj * ((h + K1_TI - 1) / K1_TI);
     const int t2 = ((W + K2_T - 1) / K2_T) * ((H + K2_T - 1) / K2_T);
     CUtensorMap map_a;
-    if (int e = make_x_map(&map_a, D.xa, B, H, W)) return e;
-    ASR_LAUNCH_TIMED(0, k_forward_residual, dim3(t1, T.max_kept, B), K1_THREADS, K1_SMEM, st, map_a, d_copies, D.resid, D.fwd, D.src, D.ip,
-                     0, N, h, w, H, W, ntj, div_magic(ntj), 0);
+    if (int e = make_x_map(&map_a, D.xa, B, H, W, T.small_box ? K1_XR_SMALL : K1_XR_BIG)) return e;
+    if (T.small_box)
+        ASR_LAUNCH_TIMED(0, k_forward_residual<K1_XR_SMALL>, dim3(t1, T.max_kept, B), K1_THREADS, k1_smem<K1_XR_SMALL>(), st, map_a, d_copies,
+                         D.resid, D.fwd, D.src, D.ip, 0, N, h, w, H, W, ntj, div_magic(ntj), 0);
+    else
+        ASR_LAUNCH_TIMED(0, k_forward_residual<K1_XR_BIG>, dim3(t1, T.max_kept, B), K1_THREADS, k1_smem<K1_XR_BIG>(), st, map_a, d_copies,
+                         D.resid, D.fwd, D.src, D.ip, 0, N, h, w, H, W, ntj, div_magic(ntj), 0);
     if (T.any_btv)
         ASR_LAUNCH_TIMED(1, (k_gradient_update<true, true>), dim3(t2, B), K2_THREADS, K2_SMEM, st, D.xa, D.xb, D.s0, D.s1, D.s2, D.resid,
                          D.inv, D.ip, D.sched, 0, N, h, w, H, W, B);
