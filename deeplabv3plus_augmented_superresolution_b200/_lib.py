@@ -54,6 +54,9 @@ SIGNATURES = {
     "asr_solve_batched": (C.c_int, [C.POINTER(AsrSolveParams), C.c_int, C.c_void_p, _fp, _fp, _u8p,
                                     C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                     C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "asr_solve_sweep": (C.c_int, [C.POINTER(AsrSolveParams), C.c_int, C.c_void_p, _fp, _fp, C.POINTER(C.c_int32),
+                                  C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                  C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "asr_loss_grad_batched": (C.c_int, [C.POINTER(AsrSolveParams), C.c_int, C.c_void_p, C.c_void_p, _fp, _fp, _u8p,
                                         C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                         C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
@@ -219,3 +222,27 @@ def loss_grad_batched(x, copies, angles, shifts, params, keep=None, workspace: O
                                       B, N, h, w, H, W, resid.data_ptr(), grad.data_ptr(), loss.data_ptr(),
                                       ws.data_ptr(), ws.numel(), _stream_ptr(torch)))
     return resid, grad, loss
+
+
+def solve_sweep(copies, angles, shifts, params_list, stack_index, want_loss: bool = False, workspace: Optional[Workspace] = None):
+    """asr_solve_sweep: len(params_list) solves, point i on stack stack_index[i] of copies [S,N,h,w]."""
+    torch = _torch()
+    L = lib()
+    assert copies.is_cuda and copies.dtype == torch.float32 and copies.is_contiguous() and copies.dim() == 4
+    S, N, h, w = copies.shape
+    H, W = 4 * h, 4 * w
+    P = len(params_list)
+    ang = _host_f32(angles, (S, N))
+    shf = _host_f32(shifts, (S, N, 2))
+    idx = np.ascontiguousarray(np.asarray(stack_index, dtype=np.int32).reshape(P))
+    arr, n = _params_array(list(params_list))
+    need = C.c_size_t()
+    check(L.asr_solve_workspace_bytes(P, N, h, w, H, W, max(int(p.num_iter) for p in params_list), C.byref(need)))
+    ws = (workspace or _default_ws).get(need.value, copies.device)
+    x = torch.empty((P, H, W), dtype=torch.float32, device=copies.device)
+    loss = torch.empty((P,), dtype=torch.float32, device=copies.device) if want_loss else None
+    with torch.cuda.device(copies.device):
+        check(L.asr_solve_sweep(arr, n, copies.data_ptr(), ang.ctypes.data_as(_fp), shf.ctypes.data_as(_fp),
+                                idx.ctypes.data_as(C.POINTER(C.c_int32)), S, N, h, w, H, W, x.data_ptr(),
+                                None if loss is None else loss.data_ptr(), ws.data_ptr(), ws.numel(), _stream_ptr(torch)))
+    return (x, loss) if want_loss else x

@@ -33,7 +33,7 @@ struct ImgParams {
     int num_iter;
     int n_kept;
     int use_btv;        // bilateral TV (superresolution.py:8-23) instead of tf.image.image_gradients TV
-    int pad0;
+    int stack;          // which LR stack of `copies` this solve reads (== image index unless a sweep shares stacks)
     float btv_w[5];     // 0.6^n, n = |h|+|v|
     float btv_lw[5];    // fl(lambda_tv * 0.6^n)
     int pad1, pad2;
@@ -47,13 +47,13 @@ constexpr int LOG2S = 2;  // HR/LR scale 4 (H == 4h): the 2x2 box of tf.image.re
 // ================================================================================================
 // K0: x0 = tf.image.resize(copies[0], (H,W))  (superresolution.py:112-113)
 // ================================================================================================
-__global__ void k_init_upsample(const float* __restrict__ copies, float* __restrict__ x0, int N, int h, int w, int H,
-                                int W) {
+__global__ void k_init_upsample(const float* __restrict__ copies, const ImgParams* __restrict__ ip, float* __restrict__ x0, int N,
+                                int h, int w, int H, int W) {
     const int b = blockIdx.z;
     const int X = blockIdx.x * blockDim.x + threadIdx.x;
     const int Y = blockIdx.y * blockDim.y + threadIdx.y;
     if (X >= W || Y >= H) return;
-    const float* img = copies + (size_t)b * N * h * w;  // copy 0 is the un-augmented one
+    const float* img = copies + (size_t)ip[b].stack * N * h * w;  // copy 0 is the un-augmented one
     const float ys = (float)h / (float)H, xs = (float)w / (float)W;
     const float in_y = fsub(fmul(fadd((float)Y, 0.5f), ys), 0.5f);
     const float in_x = fsub(fmul(fadd((float)X, 0.5f), xs), 0.5f);
@@ -241,7 +241,7 @@ k_forward_residual(const __grid_constant__ CUtensorMap xmap, const float* __rest
             D = fadd(top, fmul(fsub(bot, top), 0.5f));
         }
         const int src = src_idx[(size_t)b * N + ks];
-        resid[(((size_t)b * N + ks) * h + i) * w + j] = fsub(D, __ldg(copies + (((size_t)b * N + src) * h + i) * w + j));
+        resid[(((size_t)b * N + ks) * h + i) * w + j] = fsub(D, __ldg(copies + (((size_t)P.stack * N + src) * h + i) * w + j));
     }
 }
 
@@ -663,7 +663,7 @@ struct HostTables {
 };
 
 static void build_tables(const AsrSolveParams* params, int n_params, const float* angles, const float* shifts,
-                         const uint8_t* keep, int B, int N, int H, int W, HostTables& T) {
+                         const uint8_t* keep, const int32_t* stack_index, int B, int N, int H, int W, HostTables& T) {
     T.fwd.assign((size_t)B * N, FwdXf{});
     T.inv.assign((size_t)B * N, InvXf{});
     T.src.assign((size_t)B * N, 0);
@@ -672,14 +672,15 @@ static void build_tables(const AsrSolveParams* params, int n_params, const float
     for (int b = 0; b < B; ++b) {
         const AsrSolveParams& p = params[n_params == 1 ? 0 : b];
         T.hp[b] = p;
+        const size_t sb = stack_index ? (size_t)stack_index[b] : (size_t)b;   // angles/shifts/copies are per stack
         int kept = 0;
         for (int k = 0; k < N; ++k) {
             if (keep && !keep[(size_t)b * N + k]) continue;
             float rot[8], roti[8], tr[8], tri[8];
-            rotate_matrix(angles[(size_t)b * N + k], H, W, rot);
+            rotate_matrix(angles[sb * N + k], H, W, rot);
             invert_transform(rot, roti);
-            tr[0] = 1.0f; tr[1] = 0.0f; tr[2] = -shifts[2 * ((size_t)b * N + k)];
-            tr[3] = 0.0f; tr[4] = 1.0f; tr[5] = -shifts[2 * ((size_t)b * N + k) + 1];
+            tr[0] = 1.0f; tr[1] = 0.0f; tr[2] = -shifts[2 * (sb * N + k)];
+            tr[3] = 0.0f; tr[4] = 1.0f; tr[5] = -shifts[2 * (sb * N + k) + 1];
             tr[6] = 0.0f; tr[7] = 0.0f;
             invert_transform(tr, tri);
             const size_t o = (size_t)b * N + kept;
@@ -698,6 +699,7 @@ static void build_tables(const AsrSolveParams* params, int n_params, const float
         q.optimizer = p.optimizer; q.amsgrad = p.amsgrad; q.nesterov = p.nesterov;
         q.num_iter = p.num_iter; q.n_kept = kept;
         q.use_btv = p.use_btv ? 1 : 0;
+        q.stack = (int)sb;
         if (p.use_btv) T.any_btv = true;
         for (int n = 0; n < 5; ++n) {
             q.btv_w[n] = powf(0.6f, (float)n);
@@ -811,10 +813,9 @@ extern "C" int asr_solve_workspace_bytes(int B, int N, int h, int w, int H, int 
     return ASR_OK;
 }
 
-extern "C" int asr_solve_batched(const AsrSolveParams* params, int n_params, const float* d_copies,
-                                 const float* h_angles, const float* h_shifts, const uint8_t* h_keep, int B, int N,
-                                 int h, int w, int H, int W, float* d_x_out, float* d_loss_out, void* d_workspace,
-                                 size_t workspace_bytes, void* stream) {
+static int solve_impl(const AsrSolveParams* params, int n_params, const float* d_copies, const float* h_angles,
+                      const float* h_shifts, const uint8_t* h_keep, const int32_t* h_stack_index, int B, int N, int h, int w,
+                      int H, int W, float* d_x_out, float* d_loss_out, void* d_workspace, size_t workspace_bytes, void* stream) {
     if (!params || !d_copies || !h_angles || !h_shifts || !d_x_out || !d_workspace) return fail(ASR_ENULL, "null argument");
     if (n_params != 1 && n_params != B) return fail(ASR_EINVAL, "n_params must be 1 or B");
     if (int e = check_shapes(B, N, h, w, H, W)) return e;
@@ -822,7 +823,7 @@ extern "C" int asr_solve_batched(const AsrSolveParams* params, int n_params, con
     cudaStream_t st = static_cast<cudaStream_t>(stream);
 
     HostTables T;
-    build_tables(params, n_params, h_angles, h_shifts, h_keep, B, N, H, W, T);
+    build_tables(params, n_params, h_angles, h_shifts, h_keep, h_stack_index, B, N, H, W, T);
     const Layout L = make_layout(B, N, h, w, H, W, T.max_iter);
     if (workspace_bytes < L.total) return fail(ASR_EWORKSPACE, "workspace %zu < required %zu bytes", workspace_bytes, L.total);
     const Device D = bind(d_workspace, L);
@@ -834,7 +835,7 @@ extern "C" int asr_solve_batched(const AsrSolveParams* params, int n_params, con
     for (int b = 0; b < B; ++b)   // Adagrad slots start at initial_accumulator_value (optimizer.py:25-27)
         if (T.hp[b].optimizer == ASR_OPT_ADAGRAD)
             ASR_LAUNCH(k_fill, 64, 256, 0, st, D.s0 + (size_t)b * plane, T.hp[b].initial_accumulator_value, plane);
-    ASR_LAUNCH(k_init_upsample, dim3((W + 31) / 32, (H + 7) / 8, B), dim3(32, 8), 0, st, d_copies, D.xa, N, h, w, H, W);
+    ASR_LAUNCH(k_init_upsample, dim3((W + 31) / 32, (H + 7) / 8, B), dim3(32, 8), 0, st, d_copies, D.ip, D.xa, N, h, w, H, W);
 
     const int ntj = (w + K1_TJ - 1) / K1_TJ;
     const int t1 = ntj * ((h + K1_TI - 1) / K1_TI);
@@ -854,11 +855,11 @@ extern "C" int asr_solve_batched(const AsrSolveParams* params, int n_params, con
             float* xn = ((it & 1) ? D.xa : D.xb) + po;
             if (T.small_box)
                 ASR_LAUNCH_TIMED(0, k_forward_residual<K1_XR_SMALL>, dim3(t1, T.max_kept, nb), K1_THREADS, k1_smem<K1_XR_SMALL>(), st,
-                    (it & 1) ? map_b : map_a, d_copies + ro, D.resid + ro, D.fwd + (size_t)b0 * N, D.src + (size_t)b0 * N, D.ip + b0,
+                    (it & 1) ? map_b : map_a, d_copies, D.resid + ro, D.fwd + (size_t)b0 * N, D.src + (size_t)b0 * N, D.ip + b0,
                     it, N, h, w, H, W, ntj, div_magic(ntj), b0);
             else
                 ASR_LAUNCH_TIMED(0, k_forward_residual<K1_XR_BIG>, dim3(t1, T.max_kept, nb), K1_THREADS, k1_smem<K1_XR_BIG>(), st,
-                    (it & 1) ? map_b : map_a, d_copies + ro, D.resid + ro, D.fwd + (size_t)b0 * N, D.src + (size_t)b0 * N, D.ip + b0,
+                    (it & 1) ? map_b : map_a, d_copies, D.resid + ro, D.fwd + (size_t)b0 * N, D.src + (size_t)b0 * N, D.ip + b0,
                     it, N, h, w, H, W, ntj, div_magic(ntj), b0);
             if (T.any_btv)
                 ASR_LAUNCH_TIMED(1, (k_gradient_update<false, true>), dim3(t2, nb), K2_THREADS, K2_SMEM, st,
@@ -879,6 +880,24 @@ extern "C" int asr_solve_batched(const AsrSolveParams* params, int n_params, con
     return ASR_OK;
 }
 
+extern "C" int asr_solve_batched(const AsrSolveParams* params, int n_params, const float* d_copies,
+                                 const float* h_angles, const float* h_shifts, const uint8_t* h_keep, int B, int N,
+                                 int h, int w, int H, int W, float* d_x_out, float* d_loss_out, void* d_workspace,
+                                 size_t workspace_bytes, void* stream) {
+    return solve_impl(params, n_params, d_copies, h_angles, h_shifts, h_keep, nullptr, B, N, h, w, H, W, d_x_out, d_loss_out,
+                      d_workspace, workspace_bytes, stream);
+}
+
+extern "C" int asr_solve_sweep(const AsrSolveParams* params, int n_points, const float* d_copies, const float* h_angles,
+                               const float* h_shifts, const int32_t* h_stack_index, int n_stacks, int N, int h, int w, int H,
+                               int W, float* d_x_out, float* d_loss_out, void* d_workspace, size_t workspace_bytes, void* stream) {
+    if (!h_stack_index) return fail(ASR_ENULL, "h_stack_index is NULL");
+    for (int i = 0; i < n_points; ++i)
+        if (h_stack_index[i] < 0 || h_stack_index[i] >= n_stacks) return fail(ASR_EINVAL, "stack index %d of point %d outside [0,%d)", h_stack_index[i], i, n_stacks);
+    return solve_impl(params, n_points, d_copies, h_angles, h_shifts, nullptr, h_stack_index, n_points, N, h, w, H, W, d_x_out,
+                      d_loss_out, d_workspace, workspace_bytes, stream);
+}
+
 extern "C" int asr_loss_grad_batched(const AsrSolveParams* params, int n_params, const float* d_x, const float* d_copies,
                                      const float* h_angles, const float* h_shifts, const uint8_t* h_keep, int B, int N,
                                      int h, int w, int H, int W, float* d_resid, float* d_grad, float* d_loss_out,
@@ -892,7 +911,7 @@ extern "C" int asr_loss_grad_batched(const AsrSolveParams* params, int n_params,
     std::vector<AsrSolveParams> one(params, params + n_params);
     for (auto& p : one) p.num_iter = 1;   // a single evaluation at the supplied x
     HostTables T;
-    build_tables(one.data(), n_params, h_angles, h_shifts, h_keep, B, N, H, W, T);
+    build_tables(one.data(), n_params, h_angles, h_shifts, h_keep, nullptr, B, N, H, W, T);
     const Layout L = make_layout(B, N, h, w, H, W, 1);
     if (workspace_bytes < L.total) return fail(ASR_EWORKSPACE, "workspace %zu < required %zu bytes", workspace_bytes, L.total);
     const Device D = bind(d_workspace, L);

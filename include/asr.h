@@ -94,6 +94,14 @@ int asr_solve_batched(const AsrSolveParams* params, int n_params,
                       float* d_x_out, float* d_loss_out,
                       void* d_workspace, size_t workspace_bytes, void* stream);
 
+/* Hyper-parameter sweeps (sweep_script.py:88-130, check_robustness-style grids): n_points independent
+ * solves, point i using LR stack h_stack_index[i] of d_copies [n_stacks,N,h,w] (angles [n_stacks,N],
+ * shifts [n_stacks,N,2]) with its own params[i]; many points may share one stack without copying it.
+ * d_x_out [n_points,H,W]; workspace sized by asr_solve_workspace_bytes(n_points, ...).              */
+int asr_solve_sweep(const AsrSolveParams* params, int n_points, const float* d_copies, const float* h_angles,
+                    const float* h_shifts, const int32_t* h_stack_index, int n_stacks, int N, int h, int w, int H, int W,
+                    float* d_x_out, float* d_loss_out, void* d_workspace, size_t workspace_bytes, void* stream);
+
 /* One evaluation of loss_function's residual and tape.gradient (superresolution.py:44-100,126-133)
  * at a caller-supplied x; used by parity tests to check single steps.
  *   d_x [B,H,W] -> d_resid [B,N,h,w] (D T_k R_k x - y_k), d_grad [B,H,W] (data + TV + L2 + L1)   */

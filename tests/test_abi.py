@@ -25,7 +25,7 @@ def declared_symbols():
 
 def test_exports_every_declared_symbol(L):
     names = declared_symbols()
-    assert len(names) == len(_lib.SIGNATURES) == 15
+    assert len(names) == len(_lib.SIGNATURES) == 16
     for n in names:
         assert hasattr(L, n), f"libasr.so does not export {n}"
         assert n in _lib.SIGNATURES, f"{n} has no ctypes signature"

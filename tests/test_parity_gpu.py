@@ -116,6 +116,28 @@ def test_per_image_parameters_in_one_batch():
         assert_loss_close(float(loss[b]), lo)
 
 
+def test_sweep_points_share_stacks():
+    """config 5: a hyper-parameter grid over a few images; every (image, point) pair is an independent solve
+    reading the image's LR stack in place."""
+    copies, ang, sh = synth(2, 6, (16, 16), 0.2, 12, seed=71)
+    grid = [dict(lambda_tv=tv, learning_rate=lr, num_iter=it) for tv in (0.1, 0.3) for lr in (1e-3, 3e-3) for it in (5, 8)]
+    points = [(s, g) for s in range(2) for g in grid]
+    x, loss = A.solve_sweep(copies, ang, sh, [A.SolveParams(**g) for _, g in points], [s for s, _ in points], want_loss=True)
+    for i, (s, g) in enumerate(points):
+        xo, lo = O.augmented_superresolution(copies[s].cpu().numpy(), ang[s], sh[s], O.SolveParams(**g), output_size=(64, 64))
+        np.testing.assert_array_equal(x[i].cpu().numpy(), xo[..., 0])
+        assert_loss_close(float(loss[i]), lo)
+
+
+@pytest.mark.parametrize("n_aug", [16, 1024])
+def test_num_aug_extremes(n_aug):
+    """config 4: the copy count is a free axis (16 ... 1024); more than one 128-copy chunk in K2."""
+    copies, ang, sh = synth(1, n_aug, (16, 16), 0.15, 20, seed=81)
+    x = A.solve_batched(copies, ang, sh, A.SolveParams(num_iter=4))
+    xo, _ = O.augmented_superresolution(copies[0].cpu().numpy(), ang[0], sh[0], O.SolveParams(num_iter=4), output_size=(64, 64))
+    np.testing.assert_array_equal(x[0].cpu().numpy(), xo[..., 0])
+
+
 @pytest.mark.parametrize("name", ["small_adam", "small_value8_bigangle", "small_sgd", "canonical_config1"])
 def test_committed_goldens(name):
     """canonical_config1 = BASELINE.json configs[0]: 1 image, 100 copies, 128^2 -> 512^2, 300 Adam/AMSGrad steps."""
