@@ -145,10 +145,19 @@ def run_reference(args, rank, world):
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ---------------------------------------------------------------------------------------------------------------
+def emit(line):
+    """The one JSON line goes to the real stdout; everything else (NCCL's version banner included) was sent to stderr."""
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
+
+_REAL_STDOUT = os.dup(1)
+os.dup2(2, 1)
+
+
 def main():
     args = parse()
     rank = int(os.environ.get("RANK", "0"))
@@ -284,7 +293,7 @@ def main():
                 "clocks": clocks, "e2e": e2e, "gpu_launches": int(lt.item()), "roofline": roofline}
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(copies[0].cpu().numpy(), ang[0], sh[0], args.cpu_seconds)
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
