@@ -79,6 +79,30 @@ __device__ __forceinline__ float bilerp(float v00, float v01, float v10, float v
     return fadd(fmul(wy0, top), fmul(wy1, bot));
 }
 
+// ---- packed fp32 (sm_100a FADD2 / FMUL2) ---------------------------------------------------------
+// Two independent IEEE fp32 lanes in one 64-bit register pair.  Every packed op rounds each lane exactly
+// like its scalar counterpart (no fusion), so packing two pixels into one instruction changes nothing
+// in the result -- it halves the issue slots the arithmetic needs (measured: scripts/dev/mb_packed.cu,
+// FADD2 = 2 clk/warp on the FMA pipes while LDS / integer instructions issue in its shadow).
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pk(float lo, float hi) { f32x2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ float pk_lo(f32x2 v) { float lo, hi; asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); return lo; }
+__device__ __forceinline__ float pk_hi(f32x2 v) { float lo, hi; asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); return hi; }
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) { f32x2 r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ f32x2 sub2(f32x2 a, f32x2 b) { f32x2 r; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) { f32x2 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ f32x2 add2_rd(f32x2 a, f32x2 b) { f32x2 r; asm("add.rm.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+// bilerp() on two pixels at once.  ptxas (12.9) contracts a packed multiply feeding a packed add into FFMA2
+// even when both carry an explicit .rn (it never does so for scalar ops, nor across a scalar/packed
+// boundary), so the products are packed and the sums scalar: same FMA-pipe time, three more issue slots.
+__device__ __forceinline__ f32x2 bilerp2(f32x2 v00, f32x2 v01, f32x2 v10, f32x2 v11, f32x2 wx0, f32x2 wx1, f32x2 wy0, f32x2 wy1) {
+    const f32x2 m00 = mul2(wx0, v00), m01 = mul2(wx1, v01), m10 = mul2(wx0, v10), m11 = mul2(wx1, v11);
+    const f32x2 top = pk(fadd(pk_lo(m00), pk_lo(m01)), fadd(pk_hi(m00), pk_hi(m01)));
+    const f32x2 bot = pk(fadd(pk_lo(m10), pk_lo(m11)), fadd(pk_hi(m10), pk_hi(m11)));
+    const f32x2 n0 = mul2(wy0, top), n1 = mul2(wy1, bot);
+    return pk(fadd(pk_lo(n0), pk_lo(n1)), fadd(pk_hi(n0), pk_hi(n1)));
+}
+
 __device__ __forceinline__ float sgn(float v) { return (v > 0.0f) ? 1.0f : ((v < 0.0f) ? -1.0f : 0.0f); }
 
 __device__ __forceinline__ float warp_min(float v) {

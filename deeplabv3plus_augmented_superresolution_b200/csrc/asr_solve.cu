@@ -261,6 +261,19 @@ __device__ __forceinline__ float2 inv_translate_taps(int q, float u, int s, int 
     return ((int)f == q + s) ? make_float2(w0, w1) : make_float2(0.0f, w0);
 }
 
+// byte offset 4*(raw_y*STRIDE + raw_x) + cst4 for STRIDE = 96, as three shift-adds
+template <int STRIDE>
+__device__ __forceinline__ unsigned tap_offset(unsigned raw_x, unsigned raw_y, unsigned cst4) {
+    static_assert(STRIDE == 96, "stride 96 = 64 + 32");
+    unsigned o;
+    asm("{\n.reg .u32 t;\n"
+        "shl.b32 t, %1, 2;\n add.u32 %0, t, %3;\n"
+        "shl.b32 t, %2, 7;\n add.u32 %0, %0, t;\n"
+        "shl.b32 t, %2, 8;\n add.u32 %0, %0, t;\n}"
+        : "=r"(o) : "r"(raw_x), "r"(raw_y), "r"(cst4));
+    return o;
+}
+
 template <bool WRITE_GRAD, bool BTV>
 __global__ void __launch_bounds__(K2_THREADS, 2)
 k_gradient_update(const float* __restrict__ x_cur, float* __restrict__ x_next, float* __restrict__ s0,
@@ -288,13 +301,13 @@ k_gradient_update(const float* __restrict__ x_cur, float* __restrict__ x_next, f
     // build the tap tables, get at most a few cells: every warp does a similar amount per interval
     const int fill_slot = (tid + K2_THREADS - (K2_US + K2_UR)) & (K2_THREADS - 1);
 
-    float Xf[2], Yf[4], acc[8];
+    // the two pixels of a row (columns lane, lane+32) travel as the two lanes of packed fp32 registers
+    const float X0f = (float)(tx0 + lane), X1f = (float)(tx0 + lane + 32);
+    float Yf[4];
+    f32x2 accp[4];
 #pragma unroll
-    for (int c = 0; c < 2; ++c) Xf[c] = (float)(tx0 + lane + 32 * c);
-#pragma unroll
-    for (int r = 0; r < 4; ++r) Yf[r] = (float)(ty0 + warp + 16 * r);
-#pragma unroll
-    for (int e = 0; e < 8; ++e) acc[e] = 0.0f;
+    for (int r = 0; r < 4; ++r) { Yf[r] = (float)(ty0 + warp + 16 * r); accp[r] = pk(0.0f, 0.0f); }
+    const f32x2 magic2 = pk(kMagic, kMagic), one2 = pk(1.0f, 1.0f);
 
     for (int k0 = 0; k0 < nk; k0 += K2_CHUNK) {
         const int nc = min(K2_CHUNK, nk - k0);
@@ -365,27 +378,32 @@ k_gradient_update(const float* __restrict__ x_cur, float* __restrict__ x_next, f
                 const KBox bx = boxes[step];
                 if (!(bx.ncxy >> 16)) {
                     const InvXf T = xfs[step];
-                    unsigned cst = bx.cst + (unsigned)((step & 1) * (K2_US * K2_UR));
-                    asm volatile("" : "+r"(cst));   // opaque: keeps the address math at IADD + IMAD + LEA
-                    float ax[2], ay[2], bxr[4], byr[4];
-#pragma unroll
-                    for (int c = 0; c < 2; ++c) { ax[c] = fmul(T.b0, Xf[c]); ay[c] = fmul(T.b3, Xf[c]); }
-#pragma unroll
-                    for (int r = 0; r < 4; ++r) { bxr[r] = fmul(T.b1, Yf[r]); byr[r] = fmul(T.b4, Yf[r]); }
+                    // byte offset of tap (y0,x0) = 4*(raw_y*US + raw_x + cst) (mod 2^32), built from shifts and adds
+                    // (ALU pipe) so that the FMA pipes carry nothing but the packed arithmetic
+                    unsigned cst = (bx.cst + (unsigned)((step & 1) * (K2_US * K2_UR))) << 2;
+                    asm volatile("" : "+r"(cst));
+                    const char* utb = reinterpret_cast<const char*>(ut);
+                    const f32x2 b2p = pk(T.b2, T.b2), b5p = pk(T.b5, T.b5);
+                    // products stay scalar (a packed product feeding a packed sum would be contracted, asr_common.cuh)
+                    const f32x2 axp = pk(fmul(T.b0, X0f), fmul(T.b0, X1f)), ayp = pk(fmul(T.b3, X0f), fmul(T.b3, X1f));
 #pragma unroll
                     for (int r = 0; r < 4; ++r) {
-#pragma unroll
-                        for (int c = 0; c < 2; ++c) {
-                            const float ix = fadd(fadd(ax[c], bxr[r]), T.b2);
-                            const float iy = fadd(fadd(ay[c], byr[r]), T.b5);
-                            const Floor fx = floor_magic(ix), fy = floor_magic(iy);
-                            // (x_ceil - x) == 1 - (x - x_floor) bit for bit unless x in (-1,0), where that weight only
-                            // multiplies the tap x_floor = -1, which lies outside the canvas and is an exact zero of u
-                            const float wx1 = fsub(ix, fx.f), wx0 = fsub(1.0f, wx1);
-                            const float wy1 = fsub(iy, fy.f), wy0 = fsub(1.0f, wy1);
-                            const float* t0 = ut + ((unsigned)fy.raw * K2_US + ((unsigned)fx.raw + cst));
-                            acc[2 * r + c] = fadd(acc[2 * r + c], bilerp(t0[0], t0[1], t0[K2_US], t0[K2_US + 1], wx0, wx1, wy0, wy1));
-                        }
+                        const float bxr = fmul(T.b1, Yf[r]), byr = fmul(T.b4, Yf[r]);
+                        const f32x2 ix = add2(add2(axp, pk(bxr, bxr)), b2p);
+                        const f32x2 iy = add2(add2(ayp, pk(byr, byr)), b5p);
+                        // floor_magic on both lanes: raw bits = kMagicBits + floor, float floor = raw - magic
+                        const f32x2 tx = add2_rd(ix, magic2), ty = add2_rd(iy, magic2);
+                        const f32x2 fxf = sub2(tx, magic2), fyf = sub2(ty, magic2);
+                        // (x_ceil - x) == 1 - (x - x_floor) bit for bit unless x in (-1,0), where that weight only
+                        // multiplies the tap x_floor = -1, which lies outside the canvas and is an exact zero of u
+                        const f32x2 wx1 = sub2(ix, fxf), wx0 = sub2(one2, wx1);
+                        const f32x2 wy1 = sub2(iy, fyf), wy0 = sub2(one2, wy1);
+                        const unsigned oa = tap_offset<K2_US>(__float_as_uint(pk_lo(tx)), __float_as_uint(pk_lo(ty)), cst);
+                        const unsigned ob = tap_offset<K2_US>(__float_as_uint(pk_hi(tx)), __float_as_uint(pk_hi(ty)), cst);
+                        const float* ta = reinterpret_cast<const float*>(utb + oa);
+                        const float* tb = reinterpret_cast<const float*>(utb + ob);
+                        accp[r] = add2(accp[r], bilerp2(pk(ta[0], tb[0]), pk(ta[1], tb[1]), pk(ta[K2_US], tb[K2_US]),
+                                                        pk(ta[K2_US + 1], tb[K2_US + 1]), wx0, wx1, wy0, wy1));
                     }
                 }
             }
@@ -434,7 +452,7 @@ k_gradient_update(const float* __restrict__ x_cur, float* __restrict__ x_next, f
             if (X >= W || Y >= H) continue;
             const size_t i = (size_t)Y * W + X;
             const float xi = xc[i];
-            float g = acc[2 * r + c];
+            float g = c ? pk_hi(accp[r]) : pk_lo(accp[r]);
             if (BTV && P.use_btv) {
                 // bilateral TV: 15 integer shifts (h in [-2,2], v in [0,2]) by nearest translate with zero fill;
                 // d/dx of w*|x - S(x)| is w*sign(d) here minus the same term pulled back by the inverse shift
