@@ -86,8 +86,8 @@ __device__ __forceinline__ float bilerp(float v00, float v01, float v10, float v
 // FADD2 = 2 clk/warp on the FMA pipes while LDS / integer instructions issue in its shadow).
 typedef unsigned long long f32x2;
 __device__ __forceinline__ f32x2 pk(float lo, float hi) { f32x2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
-__device__ __forceinline__ float pk_lo(f32x2 v) { float lo, hi; asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); return lo; }
-__device__ __forceinline__ float pk_hi(f32x2 v) { float lo, hi; asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); return hi; }
+__device__ __forceinline__ float pk_lo(f32x2 v) { return __uint_as_float((unsigned)v); }
+__device__ __forceinline__ float pk_hi(f32x2 v) { return __uint_as_float((unsigned)(v >> 32)); }
 __device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) { f32x2 r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
 __device__ __forceinline__ f32x2 sub2(f32x2 a, f32x2 b) { f32x2 r; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
 __device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) { f32x2 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
@@ -138,6 +138,9 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned pari
         "bra WAIT_%=;\n"
         "DONE_%=:\n"
         "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 // one 3-D tiled tensor load global -> shared, completion counted in bytes on `bar`
 __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, int c0, int c1, int c2, unsigned long long* bar,

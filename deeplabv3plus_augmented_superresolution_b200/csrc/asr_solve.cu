@@ -110,7 +110,7 @@ template <int XR>
 __global__ void __launch_bounds__(K1_THREADS)
 k_forward_residual(const __grid_constant__ CUtensorMap xmap, const float* __restrict__ copies, float* __restrict__ resid,
                    const FwdXf* __restrict__ fwd, const int* __restrict__ src_idx,
-                   const ImgParams* __restrict__ ip, int it, int N, int h, int w, int H, int W, int ntj, unsigned ntj_magic,
+                   const ImgParams* __restrict__ ip, int it, int N, int h, int w, int wp, int H, int W, int ntj, unsigned ntj_magic,
                    int b_base) {
     const int b = blockIdx.z, ks = blockIdx.y;
     const ImgParams P = ip[b];
@@ -215,7 +215,7 @@ k_forward_residual(const __grid_constant__ CUtensorMap xmap, const float* __rest
             D = fadd(top, fmul(fsub(bot, top), 0.5f));
         }
         const int src = src_idx[(size_t)b * N + ks];
-        resid[(((size_t)b * N + ks) * h + i) * w + j] = fsub(D, __ldg(copies + (((size_t)P.stack * N + src) * h + i) * w + j));
+        resid[(((size_t)b * N + ks) * h + i) * wp + j] = fsub(D, __ldg(copies + (((size_t)P.stack * N + src) * h + i) * w + j));
     }
 }
 
@@ -225,20 +225,30 @@ k_forward_residual(const __grid_constant__ CUtensorMap xmap, const float* __rest
 // TensorFlow's gradient of the data term for copy k at HR pixel X is
 //     v_k(X) = bilinear(u_k, Rinv_k X),   u_k(q) = bilinear(g_hr, q + d_k),
 //     g_hr = ResizeBilinearGrad(2*lambda_df*r_k) = 0.25*g on the four positions {4i+1,4i+2}x{4j+1,4j+2}.
-// The CTA owns a 64x64 HR tile and loops over the copies.  For each copy it materialises u_k on the
-// bounding box of Rinv_k(tile) in shared memory, one thread per LR cell writing the 4x4 block of q
-// positions that cell feeds (q+floor(d) in [4c,4c+3]); the block's values follow the literal 2-tap
-// sums, which collapse to w_b*g / (w_a*g + w_b*g) / w_a*g / 0 by phase because the other tap reads
-// an exact zero.  Every thread then gathers 8 pixels from that tile with the op's exact arithmetic
-// and adds them to its accumulators in ascending copy order.
-// Schedule: bounding boxes and the inverse transforms of a chunk of 128 copies are computed once
-// into shared memory (one thread per copy), then each barrier interval runs, for copies k+2 / k+1 / k:
-// tap tables, u-tile fill (its residual load is prefetched before the gather) and the gather.
+// The CTA owns a 64x64 HR tile and loops over the copies with two kinds of warps:
+//   * 4 fill warps materialise u_k on the bounding box of Rinv_k(tile) in shared memory, one LR cell ->
+//     the 4x4 block of q positions that cell feeds (q+floor(d) in [4c,4c+3]); the block's values follow
+//     the literal 2-tap sums, which collapse to w_b*g / (w_a*g + w_b*g) / w_a*g / 0 by phase because the
+//     other tap reads an exact zero.  Phase 3 is a whole zero row/column of the tile: those rows are zeroed
+//     once and never rewritten.
+//   * 8 gather warps read that tile: every thread gathers 16 pixels (8 rows x the columns lane, lane+32,
+//     the column pair travelling as the two lanes of packed fp32 instructions) with the op's exact
+//     arithmetic and adds them to its accumulators in ascending copy order.
+// The two u buffers are handed back and forth with named barriers (full[2] / empty[2]: the waiting side
+// sleeps in hardware and costs no issue slots, unlike an mbarrier spin), so the fill of copy k+1 overlaps
+// the gather of copy k and the gather warps carry no bookkeeping at all.
+// Bounding boxes and the inverse transforms of a chunk of 128 copies are computed once into shared
+// memory (one thread per copy) before the roles split.
 constexpr int K2_T = 64;               // HR tile edge
-constexpr int K2_THREADS = 512;        // 16 warps; thread owns pixels (lane + 32c, warp + 16r), c<2, r<4
+constexpr int K2_GW = 8;               // gather warps; thread owns pixels (lane + 32c, warp + 8r), c<2, r<8
+constexpr int K2_FW = 4;               // fill warps
+constexpr int K2_ROWS = K2_T / K2_GW;  // rows per gather thread
+constexpr int K2_NG = 32 * K2_GW, K2_NF = 32 * K2_FW;
+constexpr int K2_THREADS = K2_NG + K2_NF;
 constexpr int K2_US = 96;              // u tile stride: 64*sqrt(2)+2+3 < 96, multiple of 32
 constexpr int K2_UR = 96;              // u tile rows
 constexpr int K2_CHUNK = 128;          // copies whose boxes/transforms are staged at once
+enum { BAR_FULL = 1, BAR_EMPTY = 3 };   // named barriers (0 is __syncthreads)
 struct __align__(16) KBox {
     unsigned cst;   // word offset folding the magic bias and the box origin (mod 2^32), buffer offset excluded
     int cbx0, cby0; // first LR cell of the box
@@ -247,8 +257,22 @@ struct __align__(16) KBox {
     int inv_ncx;    // ceil(65536 / ncx) for the cell index split
     int pad;
 };
-constexpr size_t K2_SMEM = sizeof(float) * 2 * K2_US * K2_UR + sizeof(float2) * 2 * (K2_US + K2_UR) +
-                           (sizeof(KBox) + sizeof(InvXf)) * K2_CHUNK;
+// Per-copy inputs of the fill, staged by async copies two copies ahead: the LR residual box (TMA tensor load,
+// cells outside the grid arrive as zeros) and the translate tap tables of the box's cell columns / rows.
+constexpr int K2_TPAD = 24;            // tap tables carry 24 cells of halo on both sides (boxes are <= 24 cells)
+constexpr int K2_BC = K2_US / 4;       // box cells per axis (24)
+constexpr int K2_RW = K2_BC + 4;       // residual box width: the TMA start column is rounded down to a multiple of 4
+constexpr int K2_STAGES = 4;
+struct __align__(128) K2Stage {
+    float r[K2_BC][K2_RW];             // 2688 B
+    float4 ctap[K2_BC][2];             // (wa0,wb0,wa1,wb1) (wa2,wb2,wa3,wb3) per cell column, 768 B
+    float4 rtap[K2_BC][2];             // same per cell row
+};
+constexpr unsigned K2_RBOX_BYTES = sizeof(float) * K2_BC * K2_RW, K2_TAP_BYTES = sizeof(float4) * K2_BC * 2;
+constexpr size_t K2_SMEM = sizeof(float) * 2 * K2_US * K2_UR + (sizeof(KBox) + sizeof(InvXf)) * K2_CHUNK + sizeof(K2Stage) * K2_STAGES;
+
+__device__ __forceinline__ void bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+__device__ __forceinline__ void bar_arrive(int id, int n) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 
 // literal taps of the inverse-translate gather on the window (q+s, q+s+1).  u_k is an image on the
 // HR canvas: the rotate-gradient gather zero-fills q outside [0,limit), so those columns/rows get
@@ -261,7 +285,8 @@ __device__ __forceinline__ float2 inv_translate_taps(int q, float u, int s, int 
     return ((int)f == q + s) ? make_float2(w0, w1) : make_float2(0.0f, w0);
 }
 
-// byte offset 4*(raw_y*STRIDE + raw_x) + cst4 for STRIDE = 96, as three shift-adds
+// byte offset 4*(raw_y*STRIDE + raw_x) + cst4 for STRIDE = 96, as three shift-adds (ALU pipe, the FMA
+// pipes carry nothing but the packed arithmetic)
 template <int STRIDE>
 __device__ __forceinline__ unsigned tap_offset(unsigned raw_x, unsigned raw_y, unsigned cst4) {
     static_assert(STRIDE == 96, "stride 96 = 64 + 32");
@@ -274,39 +299,65 @@ __device__ __forceinline__ unsigned tap_offset(unsigned raw_x, unsigned raw_y, u
     return o;
 }
 
+// Translate tap tables, once per solve: for copy slot k and LR cell c (with K2_TPAD cells of halo) the four
+// literal tap pairs of q = 4c - floor(u) + e, e < 4.  They depend on the transform only, not on the iterate.
+__global__ void k_tap_tables(const InvXf* __restrict__ inv, float2* __restrict__ tapc, float2* __restrict__ tapr, int N, int h,
+                             int w, int H, int W) {
+    const int k = blockIdx.y, b = blockIdx.z;
+    const int nc = 4 * (w + 2 * K2_TPAD), nr = 4 * (h + 2 * K2_TPAD);
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= nc + nr) return;
+    const InvXf T = inv[(size_t)b * N + k];
+    const size_t slot = (size_t)b * N + k;
+    if (e < nc) {
+        const int s = (int)floorf(T.ux);
+        tapc[slot * nc + e] = inv_translate_taps(4 * (e / 4 - K2_TPAD) - s + (e & 3), T.ux, s, W);
+    } else {
+        const int f = e - nc, s = (int)floorf(T.uy);
+        tapr[slot * nr + f] = inv_translate_taps(4 * (f / 4 - K2_TPAD) - s + (f & 3), T.uy, s, H);
+    }
+}
+
 template <bool WRITE_GRAD, bool BTV>
 __global__ void __launch_bounds__(K2_THREADS, 2)
-k_gradient_update(const float* __restrict__ x_cur, float* __restrict__ x_next, float* __restrict__ s0,
-                  float* __restrict__ s1, float* __restrict__ s2, const float* __restrict__ resid,
-                  const InvXf* __restrict__ inv, const ImgParams* __restrict__ ip, const Sched* __restrict__ sched,
-                  int it, int N, int h, int w, int H, int W, int B) {
+k_gradient_update(const __grid_constant__ CUtensorMap rmap, const float* __restrict__ x_cur, float* __restrict__ x_next,
+                  float* __restrict__ s0, float* __restrict__ s1, float* __restrict__ s2, const float2* __restrict__ tapc,
+                  const float2* __restrict__ tapr, const InvXf* __restrict__ inv, const ImgParams* __restrict__ ip,
+                  const Sched* __restrict__ sched, int it, int N, int h, int w, int H, int W, int B, int b_base) {
     const int b = blockIdx.y;
     const ImgParams P = ip[b];
     if (it >= P.num_iter) return;
 
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float* ut = reinterpret_cast<float*>(smem_raw);                       // [2][K2_UR][K2_US]
-    float2* colw = reinterpret_cast<float2*>(ut + 2 * K2_US * K2_UR);     // [2][K2_US]
-    float2* roww = colw + 2 * K2_US;                                      // [2][K2_UR]
-    KBox* boxes = reinterpret_cast<KBox*>(roww + 2 * K2_UR);              // [K2_CHUNK]
+    K2Stage* stages = reinterpret_cast<K2Stage*>(ut + 2 * K2_US * K2_UR);  // [K2_STAGES]
+    KBox* boxes = reinterpret_cast<KBox*>(stages + K2_STAGES);            // [K2_CHUNK]
     InvXf* xfs = reinterpret_cast<InvXf*>(boxes + K2_CHUNK);              // [K2_CHUNK]
+    __shared__ __align__(8) unsigned long long stage_bar[K2_STAGES];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int ntx = (W + K2_T - 1) / K2_T;
     const int tx0 = (blockIdx.x % ntx) * K2_T, ty0 = (blockIdx.x / ntx) * K2_T;
     const InvXf* invb = inv + (size_t)b * N;
-    const float* rb = resid + (size_t)b * N * h * w;
     const int nk = P.n_kept;
-    // u-tile cells are spread over the threads starting at warp 6, so that warps 0-5, which also
-    // build the tap tables, get at most a few cells: every warp does a similar amount per interval
-    const int fill_slot = (tid + K2_THREADS - (K2_US + K2_UR)) & (K2_THREADS - 1);
+    if (tid == 0) {
+#pragma unroll
+        for (int i = 0; i < K2_STAGES; ++i) mbar_init(&stage_bar[i], 3);   // three async copies per stage
+    }
+    const bool gather_role = warp < K2_GW;
+
+    // tile rows 3 (mod 4) hold phase 3 of every cell: zero for every copy
+    for (int i = tid; i < 2 * (K2_UR / 4) * (K2_US / 4); i += K2_THREADS) {
+        const int row = i / (K2_US / 4), c4 = i - row * (K2_US / 4);
+        reinterpret_cast<float4*>(ut + (4 * row + 3) * K2_US)[c4] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);   // rows of buffer 1 follow buffer 0
+    }
 
     // the two pixels of a row (columns lane, lane+32) travel as the two lanes of packed fp32 registers
     const float X0f = (float)(tx0 + lane), X1f = (float)(tx0 + lane + 32);
-    float Yf[4];
-    f32x2 accp[4];
+    const float Y0f = (float)(ty0 + warp);
+    f32x2 accp[K2_ROWS];
 #pragma unroll
-    for (int r = 0; r < 4; ++r) { Yf[r] = (float)(ty0 + warp + 16 * r); accp[r] = pk(0.0f, 0.0f); }
+    for (int r = 0; r < K2_ROWS; ++r) accp[r] = pk(0.0f, 0.0f);
     const f32x2 magic2 = pk(kMagic, kMagic), one2 = pk(1.0f, 1.0f);
 
     for (int k0 = 0; k0 < nk; k0 += K2_CHUNK) {
@@ -334,6 +385,7 @@ k_gradient_update(const float* __restrict__ x_cur, float* __restrict__ x_next, f
             bx.qy_lo = 4 * bx.cby0 - sy;
             const int skip = (cbx1 < 0 || bx.cbx0 >= w || cby1 < 0 || bx.cby0 >= h || 4 * ncx > K2_US || 4 * ncy > K2_UR);
             bx.ncxy = (ncx & 0xff) | ((ncy & 0xff) << 8) | (skip << 16);
+            if (skip) { bx.cbx0 = 0; bx.cby0 = 0; }   // its (unused) staging copies stay inside the tables
             bx.cst = 0u - (unsigned)(kMagicBits + bx.qy_lo) * K2_US - (unsigned)(kMagicBits + bx.qx_lo);
             bx.inv_ncx = (65536 + ncx - 1) / max(ncx, 1);
             bx.pad = 0;
@@ -342,53 +394,24 @@ k_gradient_update(const float* __restrict__ x_cur, float* __restrict__ x_next, f
         }
         __syncthreads();
 
-        for (int step = -2; step < nc; ++step) {
-            // ---- u-tile cell of copy step+1 owned by this thread: issue its residual load early --------
-            const int kc = step + 1;
-            int cell_off = -1, cyi = 0, cxi = 0;
-            float r_pref = 0.0f;
-            bool do_fill = false;
-            KBox bc;
-            if (kc >= 0 && kc < nc) {
-                bc = boxes[kc];
-                const int ncx = bc.ncxy & 0xff, ncy = (bc.ncxy >> 8) & 0xff;
-                do_fill = !(bc.ncxy >> 16) && fill_slot < ncx * ncy;
-                if (do_fill) {
-                    cyi = (fill_slot * bc.inv_ncx) >> 16;
-                    cxi = fill_slot - cyi * ncx;
-                    const int cy = bc.cby0 + cyi, cx = bc.cbx0 + cxi;
-                    if (cy >= 0 && cy < h && cx >= 0 && cx < w) {
-                        cell_off = ((k0 + kc) * h + cy) * w + cx;
-                        asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(r_pref) : "l"(rb + cell_off));   // consumed after the gather
-                    }
-                }
-            }
-            // ---- literal translate weights of copy step+2 for every q column / row of its box ----------
-            const int kt = step + 2;
-            if (kt < nc && tid < K2_US + K2_UR) {
-                const KBox bx = boxes[kt];
+        if (gather_role) {
+            // =================== gather warps ===================
+            for (int kc = 0; kc < nc; ++kc) {
+                if (kc & 1) bar_sync(BAR_FULL + 1, K2_THREADS); else bar_sync(BAR_FULL, K2_THREADS);   // u tile of copy kc is complete
+                const KBox bx = boxes[kc];
                 if (!(bx.ncxy >> 16)) {
-                    const float ux = xfs[kt].ux, uy = xfs[kt].uy;
-                    if (tid < K2_US) colw[(kt & 1) * K2_US + tid] = inv_translate_taps(bx.qx_lo + tid, ux, (int)floorf(ux), W);
-                    else roww[(kt & 1) * K2_UR + tid - K2_US] = inv_translate_taps(bx.qy_lo + tid - K2_US, uy, (int)floorf(uy), H);
-                }
-            }
-            // ---- gather copy `step` into the accumulators (ascending copy order) ------------------------
-            if (step >= 0) {
-                const KBox bx = boxes[step];
-                if (!(bx.ncxy >> 16)) {
-                    const InvXf T = xfs[step];
-                    // byte offset of tap (y0,x0) = 4*(raw_y*US + raw_x + cst) (mod 2^32), built from shifts and adds
-                    // (ALU pipe) so that the FMA pipes carry nothing but the packed arithmetic
-                    unsigned cst = (bx.cst + (unsigned)((step & 1) * (K2_US * K2_UR))) << 2;
+                    const InvXf T = xfs[kc];
+                    // byte offset of tap (y0,x0) = 4*(raw_y*US + raw_x + cst) (mod 2^32)
+                    unsigned cst = (bx.cst + (unsigned)((kc & 1) * (K2_US * K2_UR))) << 2;
                     asm volatile("" : "+r"(cst));
                     const char* utb = reinterpret_cast<const char*>(ut);
                     const f32x2 b2p = pk(T.b2, T.b2), b5p = pk(T.b5, T.b5);
                     // products stay scalar (a packed product feeding a packed sum would be contracted, asr_common.cuh)
                     const f32x2 axp = pk(fmul(T.b0, X0f), fmul(T.b0, X1f)), ayp = pk(fmul(T.b3, X0f), fmul(T.b3, X1f));
 #pragma unroll
-                    for (int r = 0; r < 4; ++r) {
-                        const float bxr = fmul(T.b1, Yf[r]), byr = fmul(T.b4, Yf[r]);
+                    for (int r = 0; r < K2_ROWS; ++r) {
+                        const float Yf = Y0f + (float)(K2_GW * r);   // exact small-integer add
+                        const float bxr = fmul(T.b1, Yf), byr = fmul(T.b4, Yf);
                         const f32x2 ix = add2(add2(axp, pk(bxr, bxr)), b2p);
                         const f32x2 iy = add2(add2(ayp, pk(byr, byr)), b5p);
                         // floor_magic on both lanes: raw bits = kMagicBits + floor, float floor = raw - magic
@@ -406,119 +429,173 @@ k_gradient_update(const float* __restrict__ x_cur, float* __restrict__ x_next, f
                                                         pk(ta[K2_US + 1], tb[K2_US + 1]), wx0, wx1, wy0, wy1));
                     }
                 }
+                // hand the buffer back; the last two hand-backs of a chunk have no taker
+                if (kc + 2 < nc) { if (kc & 1) bar_arrive(BAR_EMPTY + 1, K2_THREADS); else bar_arrive(BAR_EMPTY, K2_THREADS); }
             }
-            // ---- u tile of copy step+1: this thread's LR cell -> 4x4 block (boxes of more than 512 cells,
-            //      i.e. rotations near 45 degrees, give some threads a second, un-prefetched cell) ----------
-            if (do_fill) {
-                float* u = ut + (kc & 1) * (K2_US * K2_UR);
-                const float4* cw4 = reinterpret_cast<const float4*>(colw + (kc & 1) * K2_US);
-                const float4* rw4 = reinterpret_cast<const float4*>(roww + (kc & 1) * K2_UR);
-                const int ncx = bc.ncxy & 0xff, ncell = ncx * ((bc.ncxy >> 8) & 0xff);
-                float r = r_pref;
-                for (int c = fill_slot;;) {
-                    const float g = fmul(0.25f, fmul(P.two_ldf, r));          // g_hr on the cell's 2x2 positions
-                    const float4 ca = cw4[2 * cxi], cb = cw4[2 * cxi + 1];     // (wa0,wb0,wa1,wb1) (wa2,wb2,wa3,wb3)
-                    const float t0 = fmul(ca.y, g);                           // phase 0: taps (0, g)
-                    const float t1 = fadd(fmul(ca.z, g), fmul(ca.w, g));      // phase 1: taps (g, g)
-                    const float t2 = fmul(cb.x, g);                           // phase 2: taps (g, 0); phase 3: (0, 0)
-                    const float4 ra = rw4[2 * cyi], rc = rw4[2 * cyi + 1];
-                    float4* dst = reinterpret_cast<float4*>(u + (4 * cyi) * K2_US + 4 * cxi);
-                    dst[0] = make_float4(fmul(ra.y, t0), fmul(ra.y, t1), fmul(ra.y, t2), 0.0f);
-                    dst[K2_US / 4] = make_float4(fadd(fmul(ra.z, t0), fmul(ra.w, t0)), fadd(fmul(ra.z, t1), fmul(ra.w, t1)),
-                                                 fadd(fmul(ra.z, t2), fmul(ra.w, t2)), 0.0f);
-                    dst[2 * (K2_US / 4)] = make_float4(fmul(rc.x, t0), fmul(rc.x, t1), fmul(rc.x, t2), 0.0f);
-                    dst[3 * (K2_US / 4)] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-                    c += K2_THREADS;
-                    if (c >= ncell) break;
-                    cyi = (c * bc.inv_ncx) >> 16;
-                    cxi = c - cyi * ncx;
-                    const int cy = bc.cby0 + cyi, cx = bc.cbx0 + cxi;
-                    r = (cy >= 0 && cy < h && cx >= 0 && cx < w) ? __ldg(rb + ((k0 + kc) * h + cy) * w + cx) : 0.0f;
+        } else {
+            // =================== fill warps ===================
+            // Warp fw owns the cell rows fw, fw+4, ... of the box and lane l the cell column l (boxes are at most 24
+            // cells wide).  Everything the fill reads was staged by async copies issued two copies earlier by one
+            // thread: no address arithmetic, bounds tests or table building is left in these warps.
+            const int fw = warp - K2_GW;
+            constexpr int ROWS = (K2_BC + K2_FW - 1) / K2_FW;   // cell rows per fill warp
+            const size_t slot0 = (size_t)(b_base + b) * N + k0;
+            const int ncw = w + 2 * K2_TPAD, nrw = h + 2 * K2_TPAD;
+            auto stage_copy = [&](int kq) {   // one thread: residual box + tap rows of copy kq -> stage (k0+kq) % 4
+                const KBox bq = boxes[kq];
+                K2Stage* S = stages + ((k0 + kq) & (K2_STAGES - 1));
+                unsigned long long* bar = &stage_bar[(k0 + kq) & (K2_STAGES - 1)];
+                tma_load_3d(&S->r[0][0], &rmap, bq.cbx0 & ~3, bq.cby0, (int)(slot0 + kq), bar, K2_RBOX_BYTES);
+                bulk_load(&S->ctap[0][0], tapc + ((slot0 + kq) * ncw + bq.cbx0 + K2_TPAD) * 4, K2_TAP_BYTES, bar);
+                bulk_load(&S->rtap[0][0], tapr + ((slot0 + kq) * nrw + bq.cby0 + K2_TPAD) * 4, K2_TAP_BYTES, bar);
+            };
+            const bool issuer = (fw == 0 && lane == 0);
+            if (issuer) { stage_copy(0); if (nc > 1) stage_copy(1); }
+            for (int kc = 0; kc < nc; ++kc) {
+                const int ub = kc & 1, gk = k0 + kc;
+                const KBox bc = boxes[kc];
+                const bool live = !(bc.ncxy >> 16);
+                const int ncx = bc.ncxy & 0xff, ncy = (bc.ncxy >> 8) & 0xff;
+                if (kc >= 2) { if (ub) bar_sync(BAR_EMPTY + 1, K2_THREADS); else bar_sync(BAR_EMPTY, K2_THREADS); }   // the gather of copy kc-2 has left this buffer
+                // every fill warp is past copy kc-2 here, so the stage of copy kc+2 (the same one) is free
+                if (issuer && kc + 2 < nc) stage_copy(kc + 2);
+                mbar_wait(&stage_bar[gk & (K2_STAGES - 1)], (gk / K2_STAGES) & 1);
+                if (live && lane < ncx) {
+                    const K2Stage* S = stages + (gk & (K2_STAGES - 1));
+                    const float4 ca = S->ctap[lane][0], cb = S->ctap[lane][1];     // (wa0,wb0,wa1,wb1) (wa2,wb2,wa3,wb3)
+                    const int xo = (bc.cbx0 & 3) + lane;
+                    float4* ucol = reinterpret_cast<float4*>(ut + ub * (K2_US * K2_UR)) + lane;
+#pragma unroll
+                    for (int j = 0; j < ROWS; ++j) {
+                        const int cyi = fw + K2_FW * j;
+                        if (cyi < ncy) {
+                            const float g = fmul(0.25f, fmul(P.two_ldf, S->r[cyi][xo]));   // g_hr on the cell's 2x2 positions
+                            const float t0 = fmul(ca.y, g);                           // phase 0: taps (0, g)
+                            const float t1 = fadd(fmul(ca.z, g), fmul(ca.w, g));      // phase 1: taps (g, g)
+                            const float t2 = fmul(cb.x, g);                           // phase 2: taps (g, 0); phase 3: (0, 0)
+                            const float4 ra = S->rtap[cyi][0], rc = S->rtap[cyi][1];
+                            float4* dst = ucol + cyi * K2_US;                         // row 4*cyi
+                            dst[0] = make_float4(fmul(ra.y, t0), fmul(ra.y, t1), fmul(ra.y, t2), 0.0f);
+                            dst[K2_US / 4] = make_float4(fadd(fmul(ra.z, t0), fmul(ra.w, t0)), fadd(fmul(ra.z, t1), fmul(ra.w, t1)),
+                                                         fadd(fmul(ra.z, t2), fmul(ra.w, t2)), 0.0f);
+                            dst[2 * (K2_US / 4)] = make_float4(fmul(rc.x, t0), fmul(rc.x, t1), fmul(rc.x, t2), 0.0f);
+                        }
+                    }
                 }
+                if (ub) bar_arrive(BAR_FULL + 1, K2_THREADS); else bar_arrive(BAR_FULL, K2_THREADS);
             }
-            __syncthreads();
         }
     }
+    if (!gather_role) return;
 
     // ---- epilogue: TV (tf.image.image_gradients), L2, L1, optimizer ---------------
+    // Two rows (four pixels) at a time: every global load of the batch -- x, its four neighbours and the
+    // optimizer slots -- is issued before the first use, so a batch costs one memory round trip, not one per pixel.
     const size_t plane = (size_t)H * W;
     const float* xc = x_cur + (size_t)b * plane;
     const Sched sc = sched[(size_t)it * B + b];
+    const bool btv = BTV && P.use_btv;
+    const bool need0 = !WRITE_GRAD && !(P.optimizer == ASR_OPT_SGD && P.momentum == 0.0f);
+    const bool need1 = !WRITE_GRAD && (P.optimizer == ASR_OPT_ADAM || P.optimizer == ASR_OPT_ADADELTA || P.optimizer == ASR_OPT_ADAMAX);
+    const bool need2 = !WRITE_GRAD && P.optimizer == ASR_OPT_ADAM && P.amsgrad;
+    constexpr int EB = 2;
 #pragma unroll
-    for (int r = 0; r < 4; ++r) {
+    for (int r0 = 0; r0 < K2_ROWS; r0 += EB) {
+        float xi_[EB][2], nu_[EB][2], nl_[EB][2], nd_[EB][2], nr_[EB][2], v0_[EB][2], v1_[EB][2], v2_[EB][2];
 #pragma unroll
-        for (int c = 0; c < 2; ++c) {
-            const int X = tx0 + lane + 32 * c, Y = ty0 + warp + 16 * r;
-            if (X >= W || Y >= H) continue;
-            const size_t i = (size_t)Y * W + X;
-            const float xi = xc[i];
-            float g = c ? pk_hi(accp[r]) : pk_lo(accp[r]);
-            if (BTV && P.use_btv) {
-                // bilateral TV: 15 integer shifts (h in [-2,2], v in [0,2]) by nearest translate with zero fill;
-                // d/dx of w*|x - S(x)| is w*sign(d) here minus the same term pulled back by the inverse shift
-                for (int hh = -2; hh <= 2; ++hh) {
-                    for (int vv = 0; vv <= 2; ++vv) {
-                        const float lw = P.btv_lw[abs(hh) + vv];
-                        const int xs = X - hh, ys = Y - vv, xt = X + hh, yt = Y + vv;
-                        const float shifted = (xs >= 0 && xs < W && ys >= 0) ? xc[(size_t)ys * W + xs] : 0.0f;
-                        const float gd = fmul(lw, sgn(fsub(xi, shifted)));
-                        const float gb = (xt >= 0 && xt < W && yt < H) ? fmul(lw, sgn(fsub(xc[(size_t)yt * W + xt], xi))) : 0.0f;
-                        g = fadd(g, fsub(gd, gb));
+        for (int rr = 0; rr < EB; ++rr) {
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+                const int X = tx0 + lane + 32 * c, Y = ty0 + warp + K2_GW * (r0 + rr);
+                const bool in = X < W && Y < H;
+                const size_t i = (size_t)Y * W + X, gi = (size_t)b * plane + i;
+                xi_[rr][c] = in ? xc[i] : 0.0f;
+                nu_[rr][c] = (in && !btv && Y > 0) ? xc[i - W] : 0.0f;
+                nl_[rr][c] = (in && !btv && X > 0) ? xc[i - 1] : 0.0f;
+                nd_[rr][c] = (in && !btv && Y < H - 1) ? xc[i + W] : 0.0f;
+                nr_[rr][c] = (in && !btv && X < W - 1) ? xc[i + 1] : 0.0f;
+                v0_[rr][c] = (in && need0) ? s0[gi] : 0.0f;
+                v1_[rr][c] = (in && need1) ? s1[gi] : 0.0f;
+                v2_[rr][c] = (in && need2) ? s2[gi] : 0.0f;
+            }
+        }
+#pragma unroll
+        for (int rr = 0; rr < EB; ++rr) {
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+                const int r = r0 + rr;
+                const int X = tx0 + lane + 32 * c, Y = ty0 + warp + K2_GW * r;
+                if (X >= W || Y >= H) continue;
+                const size_t i = (size_t)Y * W + X;
+                const float xi = xi_[rr][c];
+                float g = c ? pk_hi(accp[r]) : pk_lo(accp[r]);
+                if (btv) {
+                    // bilateral TV: 15 integer shifts (h in [-2,2], v in [0,2]) by nearest translate with zero fill;
+                    // d/dx of w*|x - S(x)| is w*sign(d) here minus the same term pulled back by the inverse shift
+                    for (int hh = -2; hh <= 2; ++hh) {
+                        for (int vv = 0; vv <= 2; ++vv) {
+                            const float lw = P.btv_lw[abs(hh) + vv];
+                            const int xs = X - hh, ys = Y - vv, xt = X + hh, yt = Y + vv;
+                            const float shifted = (xs >= 0 && xs < W && ys >= 0) ? xc[(size_t)ys * W + xs] : 0.0f;
+                            const float gd = fmul(lw, sgn(fsub(xi, shifted)));
+                            const float gb = (xt >= 0 && xt < W && yt < H) ? fmul(lw, sgn(fsub(xc[(size_t)yt * W + xt], xi))) : 0.0f;
+                            g = fadd(g, fsub(gd, gb));
+                        }
                     }
-                }
-            } else {
-                if (Y > 0) g = fadd(g, fmul(P.lambda_tv, sgn(fsub(xi, xc[i - W]))));
-                if (X > 0) g = fadd(g, fmul(P.lambda_tv, sgn(fsub(xi, xc[i - 1]))));
-                if (Y < H - 1) g = fsub(g, fmul(P.lambda_tv, sgn(fsub(xc[i + W], xi))));
-                if (X < W - 1) g = fsub(g, fmul(P.lambda_tv, sgn(fsub(xc[i + 1], xi))));
-            }
-            g = fadd(g, fmul(P.lambda_l2, fmul(xi, 2.0f)));
-            if (P.lambda_l1 > 0.0f) g = fadd(g, fmul(P.lambda_l1, sgn(xi)));
-            const size_t gi = (size_t)b * plane + i;
-            if (WRITE_GRAD) { x_next[gi] = g; continue; }
-            float xn;
-            switch (P.optimizer) {
-            case ASR_OPT_SGD:
-                if (P.momentum == 0.0f) {
-                    xn = fsub(xi, fmul(sc.x, g));
                 } else {
-                    const float a = fsub(fmul(s0[gi], P.momentum), fmul(sc.x, g));
-                    s0[gi] = a;
-                    xn = P.nesterov ? fadd(xi, fsub(fmul(a, P.momentum), fmul(sc.x, g))) : fadd(xi, a);
+                    if (Y > 0) g = fadd(g, fmul(P.lambda_tv, sgn(fsub(xi, nu_[rr][c]))));
+                    if (X > 0) g = fadd(g, fmul(P.lambda_tv, sgn(fsub(xi, nl_[rr][c]))));
+                    if (Y < H - 1) g = fsub(g, fmul(P.lambda_tv, sgn(fsub(nd_[rr][c], xi))));
+                    if (X < W - 1) g = fsub(g, fmul(P.lambda_tv, sgn(fsub(nr_[rr][c], xi))));
                 }
-                break;
-            case ASR_OPT_ADAGRAD: {
-                const float a = fadd(s0[gi], fmul(g, g));
-                s0[gi] = a;
-                xn = fsub(xi, __fdiv_rn(fmul(g, sc.x), fadd(__fsqrt_rn(a), P.epsilon)));
-            } break;
-            case ASR_OPT_ADADELTA: {
-                const float rho = 0.95f, eps = 1e-7f, omr = fsub(1.0f, rho);
-                const float a = fadd(fmul(s0[gi], rho), fmul(fmul(g, g), omr));
-                s0[gi] = a;
-                const float au = s1[gi];
-                const float upd = fmul(fmul(__fsqrt_rn(fadd(au, eps)), __fdiv_rn(1.0f, __fsqrt_rn(fadd(a, eps)))), g);
-                xn = fsub(xi, fmul(upd, sc.x));
-                s1[gi] = fadd(fmul(au, rho), fmul(fmul(upd, upd), omr));
-            } break;
-            case ASR_OPT_ADAMAX: {
-                const float m = fadd(s0[gi], fmul(fsub(g, s0[gi]), P.omb1));
-                s0[gi] = m;
-                const float v = fmaxf(fmul(P.beta_2, s1[gi]), fabsf(g));
-                s1[gi] = v;
-                xn = fsub(xi, fmul(sc.y, __fdiv_rn(m, fadd(v, P.epsilon))));
-            } break;
-            default: {
-                const float m = fadd(s0[gi], fmul(fsub(g, s0[gi]), P.omb1));
-                const float v = fadd(s1[gi], fmul(fsub(fmul(g, g), s1[gi]), P.omb2));
-                s0[gi] = m;
-                s1[gi] = v;
-                float den = v;
-                if (P.amsgrad) { den = fmaxf(s2[gi], v); s2[gi] = den; }
-                xn = fsub(xi, __fdiv_rn(fmul(m, sc.y), fadd(__fsqrt_rn(den), P.epsilon)));
-            } break;
+                g = fadd(g, fmul(P.lambda_l2, fmul(xi, 2.0f)));
+                if (P.lambda_l1 > 0.0f) g = fadd(g, fmul(P.lambda_l1, sgn(xi)));
+                const size_t gi = (size_t)b * plane + i;
+                if (WRITE_GRAD) { x_next[gi] = g; continue; }
+                const float o0 = v0_[rr][c], o1 = v1_[rr][c], o2 = v2_[rr][c];
+                float xn;
+                switch (P.optimizer) {
+                case ASR_OPT_SGD:
+                    if (P.momentum == 0.0f) {
+                        xn = fsub(xi, fmul(sc.x, g));
+                    } else {
+                        const float a = fsub(fmul(o0, P.momentum), fmul(sc.x, g));
+                        s0[gi] = a;
+                        xn = P.nesterov ? fadd(xi, fsub(fmul(a, P.momentum), fmul(sc.x, g))) : fadd(xi, a);
+                    }
+                    break;
+                case ASR_OPT_ADAGRAD: {
+                    const float a = fadd(o0, fmul(g, g));
+                    s0[gi] = a;
+                    xn = fsub(xi, __fdiv_rn(fmul(g, sc.x), fadd(__fsqrt_rn(a), P.epsilon)));
+                } break;
+                case ASR_OPT_ADADELTA: {
+                    const float rho = 0.95f, eps = 1e-7f, omr = fsub(1.0f, rho);
+                    const float a = fadd(fmul(o0, rho), fmul(fmul(g, g), omr));
+                    s0[gi] = a;
+                    const float upd = fmul(fmul(__fsqrt_rn(fadd(o1, eps)), __fdiv_rn(1.0f, __fsqrt_rn(fadd(a, eps)))), g);
+                    xn = fsub(xi, fmul(upd, sc.x));
+                    s1[gi] = fadd(fmul(o1, rho), fmul(fmul(upd, upd), omr));
+                } break;
+                case ASR_OPT_ADAMAX: {
+                    const float m = fadd(o0, fmul(fsub(g, o0), P.omb1));
+                    s0[gi] = m;
+                    const float v = fmaxf(fmul(P.beta_2, o1), fabsf(g));
+                    s1[gi] = v;
+                    xn = fsub(xi, fmul(sc.y, __fdiv_rn(m, fadd(v, P.epsilon))));
+                } break;
+                default: {
+                    const float m = fadd(o0, fmul(fsub(g, o0), P.omb1));
+                    const float v = fadd(o1, fmul(fsub(fmul(g, g), o1), P.omb2));
+                    s0[gi] = m;
+                    s1[gi] = v;
+                    float den = v;
+                    if (P.amsgrad) { den = fmaxf(o2, v); s2[gi] = den; }
+                    xn = fsub(xi, __fdiv_rn(fmul(m, sc.y), fadd(__fsqrt_rn(den), P.epsilon)));
+                } break;
+                }
+                x_next[gi] = xn;
             }
-            x_next[gi] = xn;
         }
     }
 }
@@ -527,16 +604,16 @@ k_gradient_update(const float* __restrict__ x_cur, float* __restrict__ x_next, f
 // loss of one evaluation (superresolution.py:71-98), double accumulators
 // ================================================================================================
 __global__ void k_loss_terms(const float* __restrict__ xa, const float* __restrict__ xb_, const float* __restrict__ resid,
-                             const ImgParams* __restrict__ ip, double* __restrict__ accum, int N, int h, int w, int H, int W) {
+                             const ImgParams* __restrict__ ip, double* __restrict__ accum, int N, int h, int w, int wp, int H, int W) {
     const int b = blockIdx.y;
     const ImgParams P = ip[b];
     // x of the last evaluation lives in buffer (num_iter-1)&1
     const float* x = (((P.num_iter - 1) & 1) ? xb_ : xa) + (size_t)b * H * W;
-    const float* r = resid + (size_t)b * N * h * w;
-    const size_t nr = (size_t)P.n_kept * h * w, nx = (size_t)H * W;
+    const float* r = resid + (size_t)b * N * h * wp;
+    const size_t nr = (size_t)P.n_kept * h * wp, nx = (size_t)H * W;
     double df = 0.0, tv = 0.0, l2 = 0.0, l1 = 0.0;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nr; i += (size_t)gridDim.x * blockDim.x) {
-        const double v = r[i];
+        const double v = ((int)(i % wp) < w) ? r[i] : 0.0;   // pitch padding is not part of the residual
         df += v * v;
     }
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nx; i += (size_t)gridDim.x * blockDim.x) {
@@ -592,9 +669,10 @@ __global__ void k_fill(float* __restrict__ p, float v, size_t n) {
 // host orchestration
 // ================================================================================================
 static size_t align_up(size_t v, size_t a = 256) { return (v + a - 1) / a * a; }
+static int pitch4(int w) { return (w + 3) & ~3; }   // residual row pitch: TMA strides must be multiples of 16 bytes
 
 struct Layout {
-    size_t xa, xb, s0, s1, s2, resid, fwd, inv, src, ip, hp, sched, accum, total;
+    size_t xa, xb, s0, s1, s2, resid, tapc, tapr, fwd, inv, src, ip, hp, sched, accum, total;
 };
 
 static Layout make_layout(int B, int N, int h, int w, int H, int W, int max_iter) {
@@ -606,7 +684,9 @@ static Layout make_layout(int B, int N, int h, int w, int H, int W, int max_iter
     L.s0 = o; o += align_up(plane);
     L.s1 = o; o += align_up(plane);
     L.s2 = o; o += align_up(plane);
-    L.resid = o; o += align_up(sizeof(float) * (size_t)B * N * h * w);
+    L.resid = o; o += align_up(sizeof(float) * (size_t)B * N * h * pitch4(w));
+    L.tapc = o; o += align_up(sizeof(float2) * (size_t)B * N * 4 * (w + 2 * K2_TPAD));
+    L.tapr = o; o += align_up(sizeof(float2) * (size_t)B * N * 4 * (h + 2 * K2_TPAD));
     L.fwd = o; o += align_up(sizeof(FwdXf) * (size_t)B * N);
     L.inv = o; o += align_up(sizeof(InvXf) * (size_t)B * N);
     L.src = o; o += align_up(sizeof(int) * (size_t)B * N);
@@ -722,6 +802,7 @@ static void build_tables(const AsrSolveParams* params, int n_params, const float
 
 struct Device {
     float *xa, *xb, *s0, *s1, *s2, *resid;
+    float2 *tapc, *tapr;
     FwdXf* fwd; InvXf* inv; int* src; ImgParams* ip; AsrSolveParams* hp; Sched* sched; double* accum;
 };
 
@@ -731,6 +812,7 @@ static Device bind(void* ws, const Layout& L) {
     D.xa = (float*)(p + L.xa); D.xb = (float*)(p + L.xb);
     D.s0 = (float*)(p + L.s0); D.s1 = (float*)(p + L.s1); D.s2 = (float*)(p + L.s2);
     D.resid = (float*)(p + L.resid);
+    D.tapc = (float2*)(p + L.tapc); D.tapr = (float2*)(p + L.tapr);
     D.fwd = (FwdXf*)(p + L.fwd); D.inv = (InvXf*)(p + L.inv); D.src = (int*)(p + L.src);
     D.ip = (ImgParams*)(p + L.ip); D.hp = (AsrSolveParams*)(p + L.hp); D.sched = (Sched*)(p + L.sched);
     D.accum = (double*)(p + L.accum);
@@ -771,6 +853,27 @@ static int make_x_map(CUtensorMap* map, const float* base, int B, int H, int W, 
     return ASR_OK;
 }
 
+// 3-D tiled tensor map over the residuals [B*N][h][pitch] fp32 with the K2 fill box; cells outside the LR grid read as zero
+static int make_r_map(CUtensorMap* map, const float* base, int BN, int h, int w) {
+    typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                 const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    ASR_CUDA_TRY(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q));
+    if (!fn || q != cudaDriverEntryPointSuccess) return fail(ASR_ECUDA, "cuTensorMapEncodeTiled is not available in this driver");
+    const int wp = pitch4(w);
+    const cuuint64_t gdim[3] = {(cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)BN};
+    const cuuint64_t gstride[2] = {(cuuint64_t)wp * sizeof(float), (cuuint64_t)wp * h * sizeof(float)};
+    const cuuint32_t box[3] = {K2_RW, K2_BC, 1};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    const CUresult r = reinterpret_cast<EncodeFn>(fn)(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), gdim, gstride, box,
+                                                      estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                                      CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(ASR_ECUDA, "cuTensorMapEncodeTiled (residuals) failed with CUresult %d", (int)r);
+    return ASR_OK;
+}
+
 static unsigned div_magic(int d) { return (unsigned)((0x100000000ull + (unsigned)d - 1) / (unsigned)d); }   // __umulhi(n, magic) == n / d for n*d < 2^32
 
 static int configure_kernels() {
@@ -788,7 +891,7 @@ static int configure_kernels() {
 
 static int launch_loss(const Device& D, int n_params, float* d_loss, int B, int N, int h, int w, int H, int W, cudaStream_t st) {
     ASR_CUDA_TRY(cudaMemsetAsync(D.accum, 0, sizeof(double) * 4 * B, st));
-    ASR_LAUNCH(k_loss_terms, dim3(64, B), 256, 0, st, D.xa, D.xb, D.resid, D.ip, D.accum, N, h, w, H, W);
+    ASR_LAUNCH(k_loss_terms, dim3(64, B), 256, 0, st, D.xa, D.xb, D.resid, D.ip, D.accum, N, h, w, pitch4(w), H, W);
     ASR_LAUNCH(k_loss_final, (B + 127) / 128, 128, 0, st, D.accum, D.hp, d_loss, B);   // D.hp is expanded to one entry per image
     (void)n_params;
     return ASR_OK;
@@ -832,35 +935,38 @@ static int solve_impl(const AsrSolveParams* params, int n_params, const float* d
     const int ntj = (w + K1_TJ - 1) / K1_TJ;
     const int t1 = ntj * ((h + K1_TI - 1) / K1_TI);
     const int t2 = ((W + K2_T - 1) / K2_T) * ((H + K2_T - 1) / K2_T);
-    CUtensorMap map_a, map_b;
+    CUtensorMap map_a, map_b, map_r;
     const int box_rows = T.small_box ? K1_XR_SMALL : K1_XR_BIG;
+    const int wp = pitch4(w);
     if (int e = make_x_map(&map_a, D.xa, B, H, W, box_rows)) return e;
     if (int e = make_x_map(&map_b, D.xb, B, H, W, box_rows)) return e;
+    if (int e = make_r_map(&map_r, D.resid, B * N, h, w)) return e;
+    ASR_LAUNCH(k_tap_tables, dim3((4 * (w + h + 4 * K2_TPAD) + 255) / 256, N, B), 256, 0, st, D.inv, D.tapc, D.tapr, N, h, w, H, W);
     int group = params[0].images_in_flight > 0 ? params[0].images_in_flight : B;
     for (int b0 = 0; b0 < B; b0 += group) {
         const int nb = (B - b0 < group) ? B - b0 : group;
         int iters = 0;
         for (int b = b0; b < b0 + nb; ++b) iters = T.hp[b].num_iter > iters ? T.hp[b].num_iter : iters;
-        const size_t po = (size_t)b0 * plane, ro = (size_t)b0 * N * h * w;
+        const size_t po = (size_t)b0 * plane, ro = (size_t)b0 * N * h * wp;
         for (int it = 0; it < iters; ++it) {
             float* xc = ((it & 1) ? D.xb : D.xa) + po;
             float* xn = ((it & 1) ? D.xa : D.xb) + po;
             if (T.small_box)
                 ASR_LAUNCH_TIMED(0, k_forward_residual<K1_XR_SMALL>, dim3(t1, T.max_kept, nb), K1_THREADS, k1_smem<K1_XR_SMALL>(), st,
                     (it & 1) ? map_b : map_a, d_copies, D.resid + ro, D.fwd + (size_t)b0 * N, D.src + (size_t)b0 * N, D.ip + b0,
-                    it, N, h, w, H, W, ntj, div_magic(ntj), b0);
+                    it, N, h, w, wp, H, W, ntj, div_magic(ntj), b0);
             else
                 ASR_LAUNCH_TIMED(0, k_forward_residual<K1_XR_BIG>, dim3(t1, T.max_kept, nb), K1_THREADS, k1_smem<K1_XR_BIG>(), st,
                     (it & 1) ? map_b : map_a, d_copies, D.resid + ro, D.fwd + (size_t)b0 * N, D.src + (size_t)b0 * N, D.ip + b0,
-                    it, N, h, w, H, W, ntj, div_magic(ntj), b0);
+                    it, N, h, w, wp, H, W, ntj, div_magic(ntj), b0);
             if (T.any_btv)
-                ASR_LAUNCH_TIMED(1, (k_gradient_update<false, true>), dim3(t2, nb), K2_THREADS, K2_SMEM, st,
-                    xc, xn, D.s0 + po, D.s1 + po, D.s2 + po, D.resid + ro, D.inv + (size_t)b0 * N, D.ip + b0,
-                    D.sched + b0, it, N, h, w, H, W, B);
+                ASR_LAUNCH_TIMED(1, (k_gradient_update<false, true>), dim3(t2, nb), K2_THREADS, K2_SMEM, st, map_r,
+                    xc, xn, D.s0 + po, D.s1 + po, D.s2 + po, D.tapc, D.tapr, D.inv + (size_t)b0 * N, D.ip + b0,
+                    D.sched + b0, it, N, h, w, H, W, B, b0);
             else
-                ASR_LAUNCH_TIMED(1, (k_gradient_update<false, false>), dim3(t2, nb), K2_THREADS, K2_SMEM, st,
-                    xc, xn, D.s0 + po, D.s1 + po, D.s2 + po, D.resid + ro, D.inv + (size_t)b0 * N, D.ip + b0,
-                    D.sched + b0, it, N, h, w, H, W, B);
+                ASR_LAUNCH_TIMED(1, (k_gradient_update<false, false>), dim3(t2, nb), K2_THREADS, K2_SMEM, st, map_r,
+                    xc, xn, D.s0 + po, D.s1 + po, D.s2 + po, D.tapc, D.tapr, D.inv + (size_t)b0 * N, D.ip + b0,
+                    D.sched + b0, it, N, h, w, H, W, B, b0);
         }
     }
     ASR_CUDA_TRY(cudaGetLastError());
@@ -915,20 +1021,23 @@ extern "C" int asr_loss_grad_batched(const AsrSolveParams* params, int n_params,
     const int ntj = (w + K1_TJ - 1) / K1_TJ;
     const int t1 = ntj * ((h + K1_TI - 1) / K1_TI);
     const int t2 = ((W + K2_T - 1) / K2_T) * ((H + K2_T - 1) / K2_T);
-    CUtensorMap map_a;
+    CUtensorMap map_a, map_r;
+    const int wp = pitch4(w);
     if (int e = make_x_map(&map_a, D.xa, B, H, W, T.small_box ? K1_XR_SMALL : K1_XR_BIG)) return e;
+    if (int e = make_r_map(&map_r, D.resid, B * N, h, w)) return e;
+    ASR_LAUNCH(k_tap_tables, dim3((4 * (w + h + 4 * K2_TPAD) + 255) / 256, N, B), 256, 0, st, D.inv, D.tapc, D.tapr, N, h, w, H, W);
     if (T.small_box)
         ASR_LAUNCH_TIMED(0, k_forward_residual<K1_XR_SMALL>, dim3(t1, T.max_kept, B), K1_THREADS, k1_smem<K1_XR_SMALL>(), st, map_a, d_copies,
-                         D.resid, D.fwd, D.src, D.ip, 0, N, h, w, H, W, ntj, div_magic(ntj), 0);
+                         D.resid, D.fwd, D.src, D.ip, 0, N, h, w, wp, H, W, ntj, div_magic(ntj), 0);
     else
         ASR_LAUNCH_TIMED(0, k_forward_residual<K1_XR_BIG>, dim3(t1, T.max_kept, B), K1_THREADS, k1_smem<K1_XR_BIG>(), st, map_a, d_copies,
-                         D.resid, D.fwd, D.src, D.ip, 0, N, h, w, H, W, ntj, div_magic(ntj), 0);
+                         D.resid, D.fwd, D.src, D.ip, 0, N, h, w, wp, H, W, ntj, div_magic(ntj), 0);
     if (T.any_btv)
-        ASR_LAUNCH_TIMED(1, (k_gradient_update<true, true>), dim3(t2, B), K2_THREADS, K2_SMEM, st, D.xa, D.xb, D.s0, D.s1, D.s2, D.resid,
-                         D.inv, D.ip, D.sched, 0, N, h, w, H, W, B);
+        ASR_LAUNCH_TIMED(1, (k_gradient_update<true, true>), dim3(t2, B), K2_THREADS, K2_SMEM, st, map_r, D.xa, D.xb, D.s0, D.s1, D.s2,
+                         D.tapc, D.tapr, D.inv, D.ip, D.sched, 0, N, h, w, H, W, B, 0);
     else
-        ASR_LAUNCH_TIMED(1, (k_gradient_update<true, false>), dim3(t2, B), K2_THREADS, K2_SMEM, st, D.xa, D.xb, D.s0, D.s1, D.s2, D.resid,
-                         D.inv, D.ip, D.sched, 0, N, h, w, H, W, B);
+        ASR_LAUNCH_TIMED(1, (k_gradient_update<true, false>), dim3(t2, B), K2_THREADS, K2_SMEM, st, map_r, D.xa, D.xb, D.s0, D.s1, D.s2,
+                         D.tapc, D.tapr, D.inv, D.ip, D.sched, 0, N, h, w, H, W, B, 0);
     ASR_CUDA_TRY(cudaGetLastError());
     if (d_grad) ASR_CUDA_TRY(cudaMemcpyAsync(d_grad, D.xb, sizeof(float) * B * plane, cudaMemcpyDeviceToDevice, st));
     if (d_resid) {
@@ -936,9 +1045,9 @@ extern "C" int asr_loss_grad_batched(const AsrSolveParams* params, int n_params,
         ASR_CUDA_TRY(cudaMemsetAsync(d_resid, 0, sizeof(float) * (size_t)B * N * h * w, st));
         for (int b = 0; b < B; ++b)
             for (int s = 0; s < T.ip[b].n_kept; ++s)
-                ASR_CUDA_TRY(cudaMemcpyAsync(d_resid + ((size_t)b * N + T.src[(size_t)b * N + s]) * h * w,
-                                             D.resid + ((size_t)b * N + s) * h * w, sizeof(float) * h * w,
-                                             cudaMemcpyDeviceToDevice, st));
+                ASR_CUDA_TRY(cudaMemcpy2DAsync(d_resid + ((size_t)b * N + T.src[(size_t)b * N + s]) * h * w, sizeof(float) * w,
+                                               D.resid + ((size_t)b * N + s) * h * wp, sizeof(float) * wp, sizeof(float) * w, h,
+                                               cudaMemcpyDeviceToDevice, st));
     }
     if (d_loss_out) {
         if (int e = launch_loss(D, n_params, d_loss_out, B, N, h, w, H, W, st)) return e;
