@@ -234,9 +234,11 @@ k_forward_residual(const __grid_constant__ CUtensorMap xmap, const float* __rest
 //   * 8 gather warps read that tile: every thread gathers 16 pixels (8 rows x the columns lane, lane+32,
 //     the column pair travelling as the two lanes of packed fp32 instructions) with the op's exact
 //     arithmetic and adds them to its accumulators in ascending copy order.
-// The two u buffers are handed back and forth with named barriers (full[2] / empty[2]: the waiting side
-// sleeps in hardware and costs no issue slots, unlike an mbarrier spin), so the fill of copy k+1 overlaps
-// the gather of copy k and the gather warps carry no bookkeeping at all.
+// The two u buffers are handed back and forth like this: "full" is an mbarrier the fill warps arrive on and
+// each gather warp tests on its own (the fill runs ahead, so the test normally succeeds at once and the
+// gather warps never wait for each other); "empty" is a named barrier the gather warps arrive on without
+// blocking and the fill warps sleep on in hardware (no spin, no issue slots).  The fill of copy k+1 thus
+// overlaps the gather of copy k and the gather warps carry no bookkeeping at all.
 // Bounding boxes and the inverse transforms of a chunk of 128 copies are computed once into shared
 // memory (one thread per copy) before the roles split.
 constexpr int K2_T = 64;               // HR tile edge
@@ -248,7 +250,7 @@ constexpr int K2_THREADS = K2_NG + K2_NF;
 constexpr int K2_US = 96;              // u tile stride: 64*sqrt(2)+2+3 < 96, multiple of 32
 constexpr int K2_UR = 96;              // u tile rows
 constexpr int K2_CHUNK = 128;          // copies whose boxes/transforms are staged at once
-enum { BAR_FULL = 1, BAR_EMPTY = 3 };   // named barriers (0 is __syncthreads)
+enum { BAR_EMPTY = 1 };   // named barriers 1,2 (0 is __syncthreads)
 struct __align__(16) KBox {
     unsigned cst;   // word offset folding the magic bias and the box origin (mod 2^32), buffer offset excluded
     int cbx0, cby0; // first LR cell of the box
@@ -333,7 +335,7 @@ k_gradient_update(const __grid_constant__ CUtensorMap rmap, const float* __restr
     K2Stage* stages = reinterpret_cast<K2Stage*>(ut + 2 * K2_US * K2_UR);  // [K2_STAGES]
     KBox* boxes = reinterpret_cast<KBox*>(stages + K2_STAGES);            // [K2_CHUNK]
     InvXf* xfs = reinterpret_cast<InvXf*>(boxes + K2_CHUNK);              // [K2_CHUNK]
-    __shared__ __align__(8) unsigned long long stage_bar[K2_STAGES];
+    __shared__ __align__(8) unsigned long long stage_bar[K2_STAGES], full_bar[2];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int ntx = (W + K2_T - 1) / K2_T;
@@ -343,6 +345,7 @@ k_gradient_update(const __grid_constant__ CUtensorMap rmap, const float* __restr
     if (tid == 0) {
 #pragma unroll
         for (int i = 0; i < K2_STAGES; ++i) mbar_init(&stage_bar[i], 3);   // three async copies per stage
+        mbar_init(&full_bar[0], K2_FW); mbar_init(&full_bar[1], K2_FW);   // one arrival per fill warp
     }
     const bool gather_role = warp < K2_GW;
 
@@ -397,7 +400,7 @@ k_gradient_update(const __grid_constant__ CUtensorMap rmap, const float* __restr
         if (gather_role) {
             // =================== gather warps ===================
             for (int kc = 0; kc < nc; ++kc) {
-                if (kc & 1) bar_sync(BAR_FULL + 1, K2_THREADS); else bar_sync(BAR_FULL, K2_THREADS);   // u tile of copy kc is complete
+                mbar_wait(&full_bar[kc & 1], ((k0 + kc) >> 1) & 1);   // u tile of copy kc is complete (no rendezvous among the gather warps)
                 const KBox bx = boxes[kc];
                 if (!(bx.ncxy >> 16)) {
                     const InvXf T = xfs[kc];
@@ -482,7 +485,8 @@ k_gradient_update(const __grid_constant__ CUtensorMap rmap, const float* __restr
                         }
                     }
                 }
-                if (ub) bar_arrive(BAR_FULL + 1, K2_THREADS); else bar_arrive(BAR_FULL, K2_THREADS);
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&full_bar[ub]);
             }
         }
     }
