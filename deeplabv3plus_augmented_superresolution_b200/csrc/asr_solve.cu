@@ -85,12 +85,27 @@ constexpr int K1_THREADS = 192;        // 48 p-columns x 4 row groups of 9 rows
 constexpr int K1_PC = 3 * K1_TJ;       // needed p columns (48) and rows (36) per tile
 constexpr int K1_PR = 3 * K1_TI;
 constexpr int K1_PBS = K1_PC + 1;      // p buffer stride
+constexpr int K1_RPS = 10;             // row-product table stride per row group (9 rows, padded to keep pairs 8-byte aligned)
 constexpr int K1_XS = 96;              // TMA box width  (floats): 62*sqrt(2)+2+3 < 96, multiple of 32 -> conflict-free gathers
 constexpr int K1_XR_SMALL = 68;        // TMA box height when 62|sin|+46|cos|+3 <= 68 for every copy (|angle| <~ 0.36 rad): 6 CTAs/SM
 constexpr int K1_XR_BIG = 84;          // ... for any rotation: sqrt(62^2+46^2)+3 < 84: 5 CTAs/SM
 template <int XR>
 constexpr size_t k1_smem() {
-    return sizeof(float) * K1_XS * XR + sizeof(float) * (K1_PR * K1_PBS) + sizeof(float4) * (K1_TJ + K1_TI) + 16;
+    return sizeof(float) * K1_XS * XR + sizeof(float) * (K1_PR * K1_PBS) + sizeof(float4) * (K1_TJ + K1_TI) + sizeof(float) * 2 * 4 * K1_RPS + 16;
+}
+
+// byte offset 4*(raw_y*STRIDE + raw_x) + cst4 for STRIDE = 96, as three shift-adds (ALU pipe, the FMA
+// pipes carry nothing but the packed arithmetic)
+template <int STRIDE>
+__device__ __forceinline__ unsigned tap_offset(unsigned raw_x, unsigned raw_y, unsigned cst4) {
+    static_assert(STRIDE == 96, "stride 96 = 64 + 32");
+    unsigned o;
+    asm("{\n.reg .u32 t;\n"
+        "shl.b32 t, %1, 2;\n add.u32 %0, t, %3;\n"
+        "shl.b32 t, %2, 7;\n add.u32 %0, %0, t;\n"
+        "shl.b32 t, %2, 8;\n add.u32 %0, %0, t;\n}"
+        : "=r"(o) : "r"(raw_x), "r"(raw_y), "r"(cst4));
+    return o;
 }
 
 // translate stencil weights of z-column Z on the window (Z+s, Z+s+1), validity of p folded in
@@ -122,7 +137,9 @@ k_forward_residual(const __grid_constant__ CUtensorMap xmap, const float* __rest
     float* pb = xt + K1_XS * XR;                                                 // [K1_PR][K1_PBS]
     float4* colw = reinterpret_cast<float4*>(pb + K1_PR * K1_PBS);               // [K1_TJ] (w1a,w1b,w2a,w2b)
     float4* roww = colw + K1_TJ;                                                 // [K1_TI]
-    int* boxs = reinterpret_cast<int*>(roww + K1_TI);                            // bx0a, by0, empty
+    float* rpx = reinterpret_cast<float*>(roww + K1_TI);                         // [4][K1_RPS] fl(r1*qy) per needed p row
+    float* rpy = rpx + 4 * K1_RPS;                                               // [4][K1_RPS] fl(r4*qy)
+    int* boxs = reinterpret_cast<int*>(rpy + 4 * K1_RPS);                        // bx0a, by0, empty
 
     const int tid = threadIdx.x, lane = tid & 31;
     const int ti = (ntj == 1) ? (int)blockIdx.x : (int)__umulhi(blockIdx.x, ntj_magic);          // tile row (2^32/1 does not fit the magic)
@@ -159,7 +176,18 @@ k_forward_residual(const __grid_constant__ CUtensorMap xmap, const float* __rest
         const int c = tid - 96, Z1 = 4 * (i0 + c) + 1;
         const float2 a = translate_taps(Z1, T.ty, sy, H), d = translate_taps(Z1 + 1, T.ty, sy, H);
         roww[c] = make_float4(a.x, a.y, d.x, d.y);
+    } else if (tid >= 128 && tid < 128 + K1_PR) {
+        // the row products of the rotate coordinates, one per needed p row
+        const int m = tid - 128, gg = m / 9, mm = m - 9 * gg;
+        const float qyf = (float)(qy_lo + 12 * gg + 4 * (mm / 3) + (mm % 3));
+        rpx[gg * K1_RPS + mm] = fmul(T.r1, qyf);
+        rpy[gg * K1_RPS + mm] = fmul(T.r4, qyf);
     }
+    // this thread's cell of the second phase: request its LR sample now, it is consumed at the very end
+    const int ci = tid / K1_TJ, cj = tid % K1_TJ;
+    const int i = i0 + ci, j = j0 + cj;
+    float yk = 0.0f;
+    if (i < h && j < w) yk = __ldg(copies + (((size_t)P.stack * N + src_idx[(size_t)b * N + ks]) * h + i) * w + j);
     __syncthreads();   // box, barrier init and tables visible
     const bool empty = boxs[2] != 0;
 
@@ -168,32 +196,47 @@ k_forward_residual(const __grid_constant__ CUtensorMap xmap, const float* __rest
         const int pcn = tid % K1_PC, g = tid / K1_PC;             // p column, row group (9 rows = 3 cell rows each)
         const float qxf = (float)(qx_lo + 4 * (pcn / 3) + (pcn % 3));
         const float ax = fmul(T.r0, qxf), ay = fmul(T.r3, qxf);
-        const float qyf0 = (float)(qy_lo + 12 * g);
-        // word offset of tap (y0,x0) = raw_y*XS + raw_x + cst (mod 2^32); kept opaque so that the compiler
+        // byte offset of tap (y0,x0) = 4*(raw_y*XS + raw_x + cst) (mod 2^32); kept opaque so that the compiler
         // cannot split the magic constant out of it and re-add it once per tap
-        unsigned cst = 0u - (unsigned)(kMagicBits + boxs[1]) * K1_XS - (unsigned)(kMagicBits + boxs[0]);
+        unsigned cst = (0u - (unsigned)(kMagicBits + boxs[1]) * K1_XS - (unsigned)(kMagicBits + boxs[0])) << 2;
         asm volatile("" : "+r"(cst));
+        const char* xtb = reinterpret_cast<const char*>(xt);
         float* prow = pb + (9 * g) * K1_PBS + pcn;
+        const f32x2 axp = pk(ax, ax), ayp = pk(ay, ay), r2p = pk(T.r2, T.r2), r5p = pk(T.r5, T.r5);
+        const f32x2 magic2 = pk(kMagic, kMagic), one2 = pk(1.0f, 1.0f);
+        const float* rx = rpx + g * K1_RPS;
+        const float* ry = rpy + g * K1_RPS;
         mbar_wait(&bar, 0);
+        // rows (m, m+1) of the column travel as the two lanes of packed fp32 instructions (asr_common.cuh)
 #pragma unroll
-        for (int m = 0; m < 9; ++m) {
-            const float qyf = qyf0 + (float)(4 * (m / 3) + (m % 3));   // exact small-integer add
-            const float ix = fadd(fadd(ax, fmul(T.r1, qyf)), T.r2);
-            const float iy = fadd(fadd(ay, fmul(T.r4, qyf)), T.r5);
-            const Floor fx = floor_magic(ix), fy = floor_magic(iy);
+        for (int m = 0; m < 8; m += 2) {
+            const f32x2 ix = add2(add2(axp, *reinterpret_cast<const f32x2*>(rx + m)), r2p);
+            const f32x2 iy = add2(add2(ayp, *reinterpret_cast<const f32x2*>(ry + m)), r5p);
+            const f32x2 tx = add2_rd(ix, magic2), ty = add2_rd(iy, magic2);
+            const f32x2 fxf = sub2(tx, magic2), fyf = sub2(ty, magic2);
             // (x_ceil - x) == 1 - (x - x_floor) bit for bit unless x in (-1,0), where that weight only ever
             // multiplies the out-of-image tap x_floor = -1, i.e. an exact zero
+            const f32x2 wx1 = sub2(ix, fxf), wx0 = sub2(one2, wx1);
+            const f32x2 wy1 = sub2(iy, fyf), wy0 = sub2(one2, wy1);
+            const float* ta = reinterpret_cast<const float*>(xtb + tap_offset<K1_XS>(__float_as_uint(pk_lo(tx)), __float_as_uint(pk_lo(ty)), cst));
+            const float* tb = reinterpret_cast<const float*>(xtb + tap_offset<K1_XS>(__float_as_uint(pk_hi(tx)), __float_as_uint(pk_hi(ty)), cst));
+            const f32x2 o = bilerp2(pk(ta[0], tb[0]), pk(ta[1], tb[1]), pk(ta[K1_XS], tb[K1_XS]), pk(ta[K1_XS + 1], tb[K1_XS + 1]),
+                                    wx0, wx1, wy0, wy1);
+            prow[m * K1_PBS] = pk_lo(o);
+            prow[(m + 1) * K1_PBS] = pk_hi(o);
+        }
+        {   // the ninth row
+            const float ix = fadd(fadd(ax, rx[8]), T.r2), iy = fadd(fadd(ay, ry[8]), T.r5);
+            const Floor fx = floor_magic(ix), fy = floor_magic(iy);
             const float wx1 = fsub(ix, fx.f), wx0 = fsub(1.0f, wx1);
             const float wy1 = fsub(iy, fy.f), wy0 = fsub(1.0f, wy1);
-            const float* t0 = xt + ((unsigned)fy.raw * K1_XS + ((unsigned)fx.raw + cst));
-            prow[m * K1_PBS] = bilerp(t0[0], t0[1], t0[K1_XS], t0[K1_XS + 1], wx0, wx1, wy0, wy1);
+            const float* t0 = reinterpret_cast<const float*>(xtb + tap_offset<K1_XS>((unsigned)fx.raw, (unsigned)fy.raw, cst));
+            prow[8 * K1_PBS] = bilerp(t0[0], t0[1], t0[K1_XS], t0[K1_XS + 1], wx0, wx1, wy0, wy1);
         }
     }
     __syncthreads();
 
     // ---- one cell per thread: translate (2x2 z values), resize (literal lerps at 0.5), minus y ---------
-    const int ci = tid / K1_TJ, cj = tid % K1_TJ;
-    const int i = i0 + ci, j = j0 + cj;
     if (i < h && j < w) {
         float D = 0.0f;
         if (!empty) {
@@ -214,8 +257,7 @@ k_forward_residual(const __grid_constant__ CUtensorMap xmap, const float* __rest
             const float bot = fadd(bl, fmul(fsub(br, bl), 0.5f));
             D = fadd(top, fmul(fsub(bot, top), 0.5f));
         }
-        const int src = src_idx[(size_t)b * N + ks];
-        resid[(((size_t)b * N + ks) * h + i) * wp + j] = fsub(D, __ldg(copies + (((size_t)P.stack * N + src) * h + i) * w + j));
+        resid[(((size_t)b * N + ks) * h + i) * wp + j] = fsub(D, yk);
     }
 }
 
@@ -285,20 +327,6 @@ __device__ __forceinline__ float2 inv_translate_taps(int q, float u, int s, int 
     const float f = floorf(iq);
     const float w0 = fsub(fadd(f, 1.0f), iq), w1 = fsub(iq, f);
     return ((int)f == q + s) ? make_float2(w0, w1) : make_float2(0.0f, w0);
-}
-
-// byte offset 4*(raw_y*STRIDE + raw_x) + cst4 for STRIDE = 96, as three shift-adds (ALU pipe, the FMA
-// pipes carry nothing but the packed arithmetic)
-template <int STRIDE>
-__device__ __forceinline__ unsigned tap_offset(unsigned raw_x, unsigned raw_y, unsigned cst4) {
-    static_assert(STRIDE == 96, "stride 96 = 64 + 32");
-    unsigned o;
-    asm("{\n.reg .u32 t;\n"
-        "shl.b32 t, %1, 2;\n add.u32 %0, t, %3;\n"
-        "shl.b32 t, %2, 7;\n add.u32 %0, %0, t;\n"
-        "shl.b32 t, %2, 8;\n add.u32 %0, %0, t;\n}"
-        : "=r"(o) : "r"(raw_x), "r"(raw_y), "r"(cst4));
-    return o;
 }
 
 // Translate tap tables, once per solve: for copy slot k and LR cell c (with K2_TPAD cells of halo) the four
