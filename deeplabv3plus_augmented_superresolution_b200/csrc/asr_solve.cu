@@ -87,7 +87,7 @@ constexpr int K1_PR = 3 * K1_TI;
 constexpr int K1_PBS = K1_PC + 1;      // p buffer stride
 constexpr int K1_RPS = 10;             // row-product table stride per row group (9 rows, padded to keep pairs 8-byte aligned)
 constexpr int K1_XS = 96;              // TMA box width  (floats): 62*sqrt(2)+2+3 < 96, multiple of 32 -> conflict-free gathers
-constexpr int K1_XR_SMALL = 68;        // TMA box height when 62|sin|+46|cos|+3 <= 68 for every copy (|angle| <~ 0.36 rad): 6 CTAs/SM
+constexpr int K1_XR_SMALL = 60;        // TMA box height when 62|sin|+46|cos|+3 <= 60 for every copy (|angle| <~ 0.19 rad): 7 CTAs/SM
 constexpr int K1_XR_BIG = 84;          // ... for any rotation: sqrt(62^2+46^2)+3 < 84: 5 CTAs/SM
 template <int XR>
 constexpr size_t k1_smem() {
@@ -313,7 +313,8 @@ struct __align__(128) K2Stage {
     float4 rtap[K2_BC][2];             // same per cell row
 };
 constexpr unsigned K2_RBOX_BYTES = sizeof(float) * K2_BC * K2_RW, K2_TAP_BYTES = sizeof(float4) * K2_BC * 2;
-constexpr size_t K2_SMEM = sizeof(float) * 2 * K2_US * K2_UR + (sizeof(KBox) + sizeof(InvXf)) * K2_CHUNK + sizeof(K2Stage) * K2_STAGES;
+constexpr size_t K2_SMEM = sizeof(float) * 2 * K2_US * K2_UR + (sizeof(KBox) + sizeof(InvXf)) * K2_CHUNK + sizeof(K2Stage) * K2_STAGES +
+                           sizeof(float2) * 2 * K2_T;
 
 __device__ __forceinline__ void bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 __device__ __forceinline__ void bar_arrive(int id, int n) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); }
@@ -363,6 +364,7 @@ k_gradient_update(const __grid_constant__ CUtensorMap rmap, const float* __restr
     K2Stage* stages = reinterpret_cast<K2Stage*>(ut + 2 * K2_US * K2_UR);  // [K2_STAGES]
     KBox* boxes = reinterpret_cast<KBox*>(stages + K2_STAGES);            // [K2_CHUNK]
     InvXf* xfs = reinterpret_cast<InvXf*>(boxes + K2_CHUNK);              // [K2_CHUNK]
+    float2* rowp = reinterpret_cast<float2*>(xfs + K2_CHUNK);             // [2][K2_T] (fl(b1*Y), fl(b4*Y)) of the tile's rows, per u buffer
     __shared__ __align__(8) unsigned long long stage_bar[K2_STAGES], full_bar[2];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -385,7 +387,6 @@ k_gradient_update(const __grid_constant__ CUtensorMap rmap, const float* __restr
 
     // the two pixels of a row (columns lane, lane+32) travel as the two lanes of packed fp32 registers
     const float X0f = (float)(tx0 + lane), X1f = (float)(tx0 + lane + 32);
-    const float Y0f = (float)(ty0 + warp);
     f32x2 accp[K2_ROWS];
 #pragma unroll
     for (int r = 0; r < K2_ROWS; ++r) accp[r] = pk(0.0f, 0.0f);
@@ -441,8 +442,8 @@ k_gradient_update(const __grid_constant__ CUtensorMap rmap, const float* __restr
                     const f32x2 axp = pk(fmul(T.b0, X0f), fmul(T.b0, X1f)), ayp = pk(fmul(T.b3, X0f), fmul(T.b3, X1f));
 #pragma unroll
                     for (int r = 0; r < K2_ROWS; ++r) {
-                        const float Yf = Y0f + (float)(K2_GW * r);   // exact small-integer add
-                        const float bxr = fmul(T.b1, Yf), byr = fmul(T.b4, Yf);
+                        const float2 rp = rowp[(kc & 1) * K2_T + warp + K2_GW * r];   // row products, built by the fill warps
+                        const float bxr = rp.x, byr = rp.y;
                         const f32x2 ix = add2(add2(axp, pk(bxr, bxr)), b2p);
                         const f32x2 iy = add2(add2(ayp, pk(byr, byr)), b5p);
                         // floor_magic on both lanes: raw bits = kMagicBits + floor, float floor = raw - magic
@@ -512,6 +513,10 @@ k_gradient_update(const __grid_constant__ CUtensorMap rmap, const float* __restr
                             dst[2 * (K2_US / 4)] = make_float4(fmul(rc.x, t0), fmul(rc.x, t1), fmul(rc.x, t2), 0.0f);
                         }
                     }
+                }
+                if (live && tid - K2_NG < K2_T) {   // row products of the rotate coordinates for the gather warps
+                    const float Yf = (float)(ty0 + tid - K2_NG);
+                    rowp[ub * K2_T + tid - K2_NG] = make_float2(fmul(xfs[kc].b1, Yf), fmul(xfs[kc].b4, Yf));
                 }
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&full_bar[ub]);
