@@ -34,6 +34,13 @@ UNIT = "images/s"
 ITERS, NUM_AUG, LR_HW, HR_HW = 300, 100, (128, 128), (512, 512)
 # per image-iteration, read the LR-sized stack once + read/write x + read/write m, v, vhat
 BYTES_PER_IMAGE_ITER = 4 * NUM_AUG * LR_HW[0] * LR_HW[1] + 8 * 4 * HR_HW[0] * HR_HW[1]
+# DESIGN.md "Roofline": un-fusable fp32 operations the literal operator sequence needs per image-iteration --
+# 22 per (HR pixel x copy) gradient gather (4 coordinate adds, 4 floor, 4 weights, 9 lerp, 1 accumulate),
+# 21 per forward rotate gather (9 per LR cell x copy), 29 per LR cell x copy for translate+resize+residual,
+# 21 per LR cell x copy to expand the residual into the translate-gradient image
+FP32_OPS_PER_IMAGE_ITER = NUM_AUG * (22 * HR_HW[0] * HR_HW[1] + (9 * 21 + 29 + 21) * LR_HW[0] * LR_HW[1])
+FP32_LANES_PER_SM = 128
+N_SM = 148
 
 
 def parse():
@@ -281,6 +288,13 @@ def main():
                     "iteration_pair": {"achieved": images_per_launch * BYTES_PER_IMAGE_ITER / iter_s / 1e9,
                                        "frac": images_per_launch * BYTES_PER_IMAGE_ITER / iter_s / 1e9 / peaks["hbm_gbs"]},
                     "note": "the solve is FP32-issue bound, not bandwidth bound: see DESIGN.md 'Roofline' and profiles/"}
+        # the bound that actually binds: fp32 lane-operations per second against 148 SMs x 128 lanes x the SM clock under load
+        clk_hz = 1e6 * float((clocks or {}).get("sm_mhz") or peaks.get("sm_max_mhz") or 1965.0)
+        fp_peak = N_SM * FP32_LANES_PER_SM * clk_hz
+        fp_ach = images_per_launch * FP32_OPS_PER_IMAGE_ITER / iter_s
+        roofline["fp32_pipe"] = {"achieved": fp_ach / 1e12, "peak": fp_peak / 1e12, "unit": "T fp32 lane-op/s", "frac": fp_ach / fp_peak,
+                                 "ops_per_image_iteration": FP32_OPS_PER_IMAGE_ITER,
+                                 "note": "un-fused IEEE ops of the literal operator sequence (no FMA by contract); K1+K2 launch pair"}
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
                 "data": "synthetic",

@@ -63,6 +63,9 @@ CASES = [
     dict(N=4, hw=(16, 16), iters=6, seed=8, kw=dict(lambda_df=0.37, lambda_tv=0.11, lambda_l2=0.0, decay_steps=3, decay_rate=0.5)),
     dict(N=5, hw=(32, 32), iters=12, seed=12, kw=dict(use_btv=True)),                                       # bilateral TV
     dict(N=4, hw=(16, 24), iters=9, seed=13, value=8.0, kw=dict(use_btv=True, lambda_tv=0.05, lambda_l1=0.01, amsgrad=False)),
+    dict(N=5, hw=(18, 22), iters=7, angle_max=0.4, shift_max=15, seed=14),                      # LR width not a multiple of 4: padded residual pitch
+    dict(N=4, hw=(15, 17), iters=6, angle_max=1.2, shift_max=10, seed=15, value=8.0),           # odd sizes
+    dict(N=131, hw=(16, 16), iters=3, angle_max=0.8, shift_max=30, seed=16),                    # odd copy count over two K2 chunks
 ]
 
 
@@ -127,6 +130,17 @@ def test_sweep_points_share_stacks():
         xo, lo = O.augmented_superresolution(copies[s].cpu().numpy(), ang[s], sh[s], O.SolveParams(**g), output_size=(64, 64))
         np.testing.assert_array_equal(x[i].cpu().numpy(), xo[..., 0])
         assert_loss_close(float(loss[i]), lo)
+
+
+def test_images_in_flight_groups():
+    """launch groups (images_in_flight) address residuals and tap tables by absolute image index"""
+    copies, ang, sh = synth(5, 6, (16, 20), 0.3, 20, seed=91)
+    x = A.solve_batched(copies, ang, sh, A.SolveParams(num_iter=6, images_in_flight=2))
+    x1 = A.solve_batched(copies, ang, sh, A.SolveParams(num_iter=6))
+    np.testing.assert_array_equal(x.cpu().numpy(), x1.cpu().numpy())
+    for b in (0, 3, 4):
+        xo, _ = O.augmented_superresolution(copies[b].cpu().numpy(), ang[b], sh[b], O.SolveParams(num_iter=6), output_size=(64, 80))
+        np.testing.assert_array_equal(x[b].cpu().numpy(), xo[..., 0])
 
 
 @pytest.mark.parametrize("n_aug", [16, 1024])
