@@ -415,7 +415,9 @@ k_gradient_update(const __grid_constant__ CUtensorMap rmap, const float* __restr
             const int ncx = cbx1 - bx.cbx0 + 1, ncy = cby1 - bx.cby0 + 1;
             bx.qx_lo = 4 * bx.cbx0 - sx;
             bx.qy_lo = 4 * bx.cby0 - sy;
-            const int skip = (cbx1 < 0 || bx.cbx0 >= w || cby1 < 0 || bx.cby0 >= h || 4 * ncx > K2_US || 4 * ncy > K2_UR);
+            const int skip = (cbx1 < 0 || bx.cbx0 >= w || cby1 < 0 || bx.cby0 >= h);
+            // a 64x64 tile rotates into at most 64*sqrt(2)+5 < 96 source rows/columns: a box that does not fit is a bug, not data
+            if (!skip && (4 * ncx > K2_US || 4 * ncy > K2_UR)) __trap();
             bx.ncxy = (ncx & 0xff) | ((ncy & 0xff) << 8) | (skip << 16);
             if (skip) { bx.cbx0 = 0; bx.cby0 = 0; }   // its (unused) staging copies stay inside the tables
             bx.cst = 0u - (unsigned)(kMagicBits + bx.qy_lo) * K2_US - (unsigned)(kMagicBits + bx.qx_lo);
