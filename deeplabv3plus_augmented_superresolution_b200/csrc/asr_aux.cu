@@ -322,6 +322,190 @@ k_backproject(const float* __restrict__ copies, const BackXf* __restrict__ xf, f
     out[((size_t)b * H + Y) * W + X] = accv;
 }
 
+// ---- tiled form (output == 4 x feature size) -----------------------------------------------------
+// One CTA per 64x64 output tile, looping over the copies.  Per copy the three ops are evaluated stage by stage
+// on the bounding box of the rotated tile instead of 4 x 4 x 4 nested taps per pixel:
+//   T  = the x-lerp of tf.image.resize on the LR rows the box touches          (LR rows x box columns + 1)
+//   U  = the y-lerp: the upsampled image on the box (+1 row/column for the translate taps)
+//   Z  = tfa.image.translate of U with per-column / per-row literal tap tables (zero outside the canvas)
+//   out = max / mean over copies of the packed-fp32 rotate gather from Z      (same gather as the solve's K2)
+// Every value is produced by the same fp32 expression as the nested form, so the two are bit-identical.
+constexpr int K5_T = 64;               // output tile edge
+constexpr int K5_THREADS = 512;        // thread owns pixels (lane + 32c, warp + 16r), c<2, r<4
+constexpr int K5_ZS = 96;              // Z stride and rows: 64*sqrt(2)+2+3 < 96, multiple of 32
+constexpr int K5_BC = K5_ZS / 4;       // box cells per axis (24)
+constexpr int K5_US = 100;             // U / T stride (97 columns)
+constexpr int K5_CHUNK = 128;
+struct __align__(16) K5Box { unsigned cst; int cbx0, cby0, ncxy, qx_lo, qy_lo, pad0, pad1; };
+constexpr size_t K5_SMEM = sizeof(float) * (K5_ZS * K5_ZS + (K5_ZS + 1) * K5_US + (K5_BC + 2) * K5_US) + sizeof(float2) * 2 * K5_ZS +
+                           (sizeof(K5Box) + sizeof(BackXf)) * K5_CHUNK;
+
+__global__ void __launch_bounds__(K5_THREADS, 2)
+k_backproject_tiled(const float* __restrict__ copies, const BackXf* __restrict__ xf, float* __restrict__ out, int mode, int N, int h,
+                    int w, int H, int W) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float* Zt = reinterpret_cast<float*>(smem_raw);                 // [K5_ZS][K5_ZS]
+    float* Ut = Zt + K5_ZS * K5_ZS;                                 // [K5_ZS + 1][K5_US]
+    float* Tt = Ut + (K5_ZS + 1) * K5_US;                           // [K5_BC + 2][K5_US]
+    float2* colw = reinterpret_cast<float2*>(Tt + (K5_BC + 2) * K5_US);   // [K5_ZS]
+    float2* roww = colw + K5_ZS;                                    // [K5_ZS]
+    K5Box* boxes = reinterpret_cast<K5Box*>(roww + K5_ZS);          // [K5_CHUNK]
+    BackXf* xfs = reinterpret_cast<BackXf*>(boxes + K5_CHUNK);      // [K5_CHUNK]
+
+    const int b = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int ntx = (W + K5_T - 1) / K5_T;
+    const int tx0 = (blockIdx.x % ntx) * K5_T, ty0 = (blockIdx.x / ntx) * K5_T;
+    const BackXf* xfb = xf + (size_t)b * N;
+    const float X0f = (float)(tx0 + lane), X1f = (float)(tx0 + lane + 32);
+    f32x2 accp[4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) accp[r] = pk(0.0f, 0.0f);
+    const f32x2 magic2 = pk(kMagic, kMagic), one2 = pk(1.0f, 1.0f);
+
+    for (int k0 = 0; k0 < N; k0 += K5_CHUNK) {
+        const int nc = min(K5_CHUNK, N - k0);
+        __syncthreads();
+        // bounding box of R(tile) per copy: each rounded op of the coordinate is monotone, the corners bound every tap
+        if (tid < nc) {
+            const BackXf T = xfb[k0 + tid];
+            float xmin = INFINITY, xmax = -INFINITY, ymin = INFINITY, ymax = -INFINITY;
+#pragma unroll
+            for (int cnr = 0; cnr < 4; ++cnr) {
+                const float X = (float)(tx0 + ((cnr & 1) ? K5_T - 1 : 0)), Y = (float)(ty0 + ((cnr & 2) ? K5_T - 1 : 0));
+                const float cix = affine_coord(T.r0, X, T.r1, Y, T.r2), ciy = affine_coord(T.r3, X, T.r4, Y, T.r5);
+                xmin = fminf(xmin, cix); xmax = fmaxf(xmax, cix); ymin = fminf(ymin, ciy); ymax = fmaxf(ymax, ciy);
+            }
+            const int qx0 = (int)floorf(xmin), qx1 = (int)floorf(xmax) + 1, qy0 = (int)floorf(ymin), qy1 = (int)floorf(ymax) + 1;
+            const int sx = (int)floorf(T.tx), sy = (int)floorf(T.ty);
+            K5Box bx;
+            bx.cbx0 = (qx0 + sx) >> 2;
+            bx.cby0 = (qy0 + sy) >> 2;
+            const int cbx1 = (qx1 + sx) >> 2, cby1 = (qy1 + sy) >> 2;
+            const int ncx = cbx1 - bx.cbx0 + 1, ncy = cby1 - bx.cby0 + 1;
+            bx.qx_lo = 4 * bx.cbx0 - sx;
+            bx.qy_lo = 4 * bx.cby0 - sy;
+            // skip: no base tap of the box lies on the canvas, Z == 0
+            const int skip = (cbx1 < 0 || bx.cbx0 >= w || cby1 < 0 || bx.cby0 >= h);
+            if (!skip && (ncx > K5_BC || ncy > K5_BC)) __trap();
+            bx.ncxy = (ncx & 0xff) | ((ncy & 0xff) << 8) | (skip << 16);
+            bx.cst = (0u - (unsigned)(kMagicBits + bx.qy_lo) * K5_ZS - (unsigned)(kMagicBits + bx.qx_lo)) << 2;
+            bx.pad0 = bx.pad1 = 0;
+            boxes[tid] = bx;
+            xfs[tid] = T;
+        }
+        __syncthreads();
+
+        for (int kc = 0; kc < nc; ++kc) {
+            const K5Box bx = boxes[kc];
+            const BackXf T = xfs[kc];
+            const bool live = !(bx.ncxy >> 16);
+            f32x2 v[4];
+#pragma unroll
+            for (int r = 0; r < 4; ++r) v[r] = pk(0.0f, 0.0f);
+            if (live) {
+                const int ncx = bx.ncxy & 0xff, ncy = (bx.ncxy >> 8) & 0xff;
+                const int nux = 4 * ncx + 1, nuy = 4 * ncy + 1;           // U extent: HR positions 4*cb0 ... 4*cb0 + 4*nc
+                const float* yk = copies + ((size_t)b * N + k0 + kc) * h * w;
+                // ---- tap tables of the translate (source validity and the canvas of Z folded in) + T ---------
+                if (tid < 2 * K5_ZS) {
+                    const bool col = tid < K5_ZS;
+                    const int e = col ? tid : tid - K5_ZS;
+                    const int q = (col ? bx.qx_lo : bx.qy_lo) + e, lim = col ? W : H;
+                    const float t = col ? T.tx : T.ty;
+                    float2 wv = make_float2(0.0f, 0.0f);
+                    if (q >= 0 && q < lim) wv = warp_taps(q, t, (int)floorf(t), lim, ASR_INTERP_BILINEAR);
+                    (col ? colw : roww)[e] = wv;
+                }
+                const float xs = (float)w / (float)W, ys = (float)h / (float)H;
+                for (int e = tid; e < (ncy + 2) * nux; e += K5_THREADS) {
+                    const int ry = e / nux, ex = e - ry * nux;
+                    const int lr = bx.cby0 - 1 + ry, mx = 4 * bx.cbx0 + ex;
+                    float tv = 0.0f;
+                    if (lr >= 0 && lr < h && mx >= 0 && mx < W) {
+                        const float in_x = fsub(fmul(fadd((float)mx, 0.5f), xs), 0.5f);
+                        const float fx = floorf(in_x);
+                        const int x0 = max((int)fx, 0), x1 = min((int)ceilf(in_x), w - 1);
+                        const float xl = fsub(in_x, fx);
+                        const float tl = __ldg(yk + lr * w + x0), tr = __ldg(yk + lr * w + x1);
+                        tv = fadd(tl, fmul(fsub(tr, tl), xl));
+                    }
+                    Tt[ry * K5_US + ex] = tv;
+                }
+                __syncthreads();
+                // ---- U = upsampled image on the box ---------------------------------------------------------
+                for (int e = tid; e < nuy * nux; e += K5_THREADS) {
+                    const int ey = e / nux, ex = e - ey * nux;
+                    const int my = 4 * bx.cby0 + ey, mx = 4 * bx.cbx0 + ex;
+                    float uv = 0.0f;
+                    if (my >= 0 && my < H && mx >= 0 && mx < W) {
+                        const float in_y = fsub(fmul(fadd((float)my, 0.5f), ys), 0.5f);
+                        const float fy = floorf(in_y);
+                        const int y0 = max((int)fy, 0), y1 = min((int)ceilf(in_y), h - 1);
+                        const float yl = fsub(in_y, fy);
+                        const float t = Tt[(y0 - bx.cby0 + 1) * K5_US + ex], bb = Tt[(y1 - bx.cby0 + 1) * K5_US + ex];
+                        uv = fadd(t, fmul(fsub(bb, t), yl));
+                    }
+                    Ut[ey * K5_US + ex] = uv;
+                }
+                __syncthreads();
+                // ---- Z = translate(U) on the box ------------------------------------------------------------
+                const int nzx = 4 * ncx;
+                for (int e = tid; e < 4 * ncy * nzx; e += K5_THREADS) {
+                    const int ey = e / nzx, ex = e - ey * nzx;
+                    const float2 wc = colw[ex], wr = roww[ey];
+                    const float* u0 = Ut + ey * K5_US + ex;
+                    Zt[ey * K5_ZS + ex] = bilerp(u0[0], u0[1], u0[K5_US], u0[K5_US + 1], wc.x, wc.y, wr.x, wr.y);
+                }
+                __syncthreads();
+                // ---- rotate gather (packed fp32: the two lanes are columns lane, lane+32) ----------------------
+                const char* zb = reinterpret_cast<const char*>(Zt);
+                const f32x2 r2p = pk(T.r2, T.r2), r5p = pk(T.r5, T.r5);
+                const f32x2 axp = pk(fmul(T.r0, X0f), fmul(T.r0, X1f)), ayp = pk(fmul(T.r3, X0f), fmul(T.r3, X1f));
+                unsigned cst = bx.cst;
+                asm volatile("" : "+r"(cst));
+#pragma unroll
+                for (int r = 0; r < 4; ++r) {
+                    const float Yf = (float)(ty0 + warp + 16 * r);
+                    const float bxr = fmul(T.r1, Yf), byr = fmul(T.r4, Yf);
+                    const f32x2 ix = add2(add2(axp, pk(bxr, bxr)), r2p);
+                    const f32x2 iy = add2(add2(ayp, pk(byr, byr)), r5p);
+                    const f32x2 txx = add2_rd(ix, magic2), tyy = add2_rd(iy, magic2);
+                    const f32x2 fxf = sub2(txx, magic2), fyf = sub2(tyy, magic2);
+                    // (x_ceil - x) == 1 - (x - x_floor) bit for bit unless x in (-1,0), where that weight only multiplies
+                    // the tap x_floor = -1, which lies outside the canvas and is an exact zero of Z
+                    const f32x2 wx1 = sub2(ix, fxf), wx0 = sub2(one2, wx1);
+                    const f32x2 wy1 = sub2(iy, fyf), wy0 = sub2(one2, wy1);
+                    const float* ta = reinterpret_cast<const float*>(zb + tap_offset<K5_ZS>(__float_as_uint(pk_lo(txx)), __float_as_uint(pk_lo(tyy)), cst));
+                    const float* tb = reinterpret_cast<const float*>(zb + tap_offset<K5_ZS>(__float_as_uint(pk_hi(txx)), __float_as_uint(pk_hi(tyy)), cst));
+                    v[r] = bilerp2(pk(ta[0], tb[0]), pk(ta[1], tb[1]), pk(ta[K5_ZS], tb[K5_ZS]), pk(ta[K5_ZS + 1], tb[K5_ZS + 1]),
+                                   wx0, wx1, wy0, wy1);
+                }
+            }
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                if (mode == ASR_BACKPROJECT_MAX) {
+                    accp[r] = (k0 + kc == 0) ? v[r] : pk(fmaxf(pk_lo(accp[r]), pk_lo(v[r])), fmaxf(pk_hi(accp[r]), pk_hi(v[r])));
+                } else {
+                    accp[r] = add2(accp[r], v[r]);
+                }
+            }
+            // the next copy's first write to Z comes after two more barriers; T and U are dead here
+        }
+    }
+    float* ob = out + (size_t)b * H * W;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+            const int X = tx0 + lane + 32 * c, Y = ty0 + warp + 16 * r;
+            if (X >= W || Y >= H) continue;
+            float a = c ? pk_hi(accp[r]) : pk_lo(accp[r]);
+            if (mode == ASR_BACKPROJECT_MEAN) a = __fdiv_rn(a, (float)N);
+            ob[(size_t)Y * W + X] = a;
+        }
+    }
+}
+
 // ================================================================================================
 // single_class_IOU counts (utils.py:180-204): per image inter/union for `class_id` and, with
 // include_bg, for class 0 after relabelling every other ground-truth class to background
@@ -472,7 +656,17 @@ extern "C" int asr_backproject_batched(int mode, const float* d_copies, const fl
     BackXf* d_xf = nullptr;
     ASR_CUDA_TRY(cudaMallocAsync((void**)&d_xf, sizeof(BackXf) * xf.size(), st));
     ASR_CUDA_TRY(cudaMemcpyAsync(d_xf, xf.data(), sizeof(BackXf) * xf.size(), cudaMemcpyHostToDevice, st));
-    ASR_LAUNCH(k_backproject, dim3((W + 31) / 32, (H + 7) / 8, B), 256, 0, st, d_copies, d_xf, d_out, mode, N, h, w, H, W);
+    if (H == 4 * h && W == 4 * w) {
+        static bool attr = false;
+        if (!attr) {
+            ASR_CUDA_TRY(cudaFuncSetAttribute(k_backproject_tiled, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K5_SMEM));
+            attr = true;
+        }
+        const int tiles = ((W + K5_T - 1) / K5_T) * ((H + K5_T - 1) / K5_T);
+        ASR_LAUNCH(k_backproject_tiled, dim3(tiles, B), K5_THREADS, K5_SMEM, st, d_copies, d_xf, d_out, mode, N, h, w, H, W);
+    } else {
+        ASR_LAUNCH(k_backproject, dim3((W + 31) / 32, (H + 7) / 8, B), 256, 0, st, d_copies, d_xf, d_out, mode, N, h, w, H, W);
+    }
     ASR_CUDA_TRY(cudaGetLastError());
     ASR_CUDA_TRY(cudaFreeAsync(d_xf, st));
     return ASR_OK;

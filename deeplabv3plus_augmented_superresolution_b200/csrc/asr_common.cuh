@@ -103,6 +103,20 @@ __device__ __forceinline__ f32x2 bilerp2(f32x2 v00, f32x2 v01, f32x2 v10, f32x2 
     return pk(fadd(pk_lo(n0), pk_lo(n1)), fadd(pk_hi(n0), pk_hi(n1)));
 }
 
+// byte offset 4*(raw_y*STRIDE + raw_x) + cst4 for STRIDE = 96, as three shift-adds (ALU pipe, the FMA
+// pipes carry nothing but the packed arithmetic)
+template <int STRIDE>
+__device__ __forceinline__ unsigned tap_offset(unsigned raw_x, unsigned raw_y, unsigned cst4) {
+    static_assert(STRIDE == 96, "stride 96 = 64 + 32");
+    unsigned o;
+    asm("{\n.reg .u32 t;\n"
+        "shl.b32 t, %1, 2;\n add.u32 %0, t, %3;\n"
+        "shl.b32 t, %2, 7;\n add.u32 %0, %0, t;\n"
+        "shl.b32 t, %2, 8;\n add.u32 %0, %0, t;\n}"
+        : "=r"(o) : "r"(raw_x), "r"(raw_y), "r"(cst4));
+    return o;
+}
+
 __device__ __forceinline__ float sgn(float v) { return (v > 0.0f) ? 1.0f : ((v < 0.0f) ? -1.0f : 0.0f); }
 
 __device__ __forceinline__ float warp_min(float v) {

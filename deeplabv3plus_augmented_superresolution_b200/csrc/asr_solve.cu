@@ -94,20 +94,6 @@ constexpr size_t k1_smem() {
     return sizeof(float) * K1_XS * XR + sizeof(float) * (K1_PR * K1_PBS) + sizeof(float4) * (K1_TJ + K1_TI) + sizeof(float) * 2 * 4 * K1_RPS + 16;
 }
 
-// byte offset 4*(raw_y*STRIDE + raw_x) + cst4 for STRIDE = 96, as three shift-adds (ALU pipe, the FMA
-// pipes carry nothing but the packed arithmetic)
-template <int STRIDE>
-__device__ __forceinline__ unsigned tap_offset(unsigned raw_x, unsigned raw_y, unsigned cst4) {
-    static_assert(STRIDE == 96, "stride 96 = 64 + 32");
-    unsigned o;
-    asm("{\n.reg .u32 t;\n"
-        "shl.b32 t, %1, 2;\n add.u32 %0, t, %3;\n"
-        "shl.b32 t, %2, 7;\n add.u32 %0, %0, t;\n"
-        "shl.b32 t, %2, 8;\n add.u32 %0, %0, t;\n}"
-        : "=r"(o) : "r"(raw_x), "r"(raw_y), "r"(cst4));
-    return o;
-}
-
 // translate stencil weights of z-column Z on the window (Z+s, Z+s+1), validity of p folded in
 __device__ __forceinline__ float2 translate_taps(int Z, float t, int s, int limit) {
     const float iz = fadd((float)Z, t);  // (1*Z + 0*Zy) + t
