@@ -337,8 +337,9 @@ constexpr int K5_BC = K5_ZS / 4;       // box cells per axis (24)
 constexpr int K5_US = 100;             // U / T stride (97 columns)
 constexpr int K5_CHUNK = 128;
 struct __align__(16) K5Box { unsigned cst; int cbx0, cby0, ncxy, qx_lo, qy_lo, pad0, pad1; };
+struct __align__(16) K5Lerp { int i0, i1; float l; int ok; };   // tf.image.resize of one HR column / row: LR taps, weight, on-canvas
 constexpr size_t K5_SMEM = sizeof(float) * (K5_ZS * K5_ZS + (K5_ZS + 1) * K5_US + (K5_BC + 2) * K5_US) + sizeof(float2) * 2 * K5_ZS +
-                           (sizeof(K5Box) + sizeof(BackXf)) * K5_CHUNK;
+                           sizeof(K5Lerp) * 2 * K5_US + (sizeof(K5Box) + sizeof(BackXf)) * K5_CHUNK;
 
 __global__ void __launch_bounds__(K5_THREADS, 2)
 k_backproject_tiled(const float* __restrict__ copies, const BackXf* __restrict__ xf, float* __restrict__ out, int mode, int N, int h,
@@ -349,7 +350,9 @@ k_backproject_tiled(const float* __restrict__ copies, const BackXf* __restrict__
     float* Tt = Ut + (K5_ZS + 1) * K5_US;                           // [K5_BC + 2][K5_US]
     float2* colw = reinterpret_cast<float2*>(Tt + (K5_BC + 2) * K5_US);   // [K5_ZS]
     float2* roww = colw + K5_ZS;                                    // [K5_ZS]
-    K5Box* boxes = reinterpret_cast<K5Box*>(roww + K5_ZS);          // [K5_CHUNK]
+    K5Lerp* lx = reinterpret_cast<K5Lerp*>(roww + K5_ZS);           // [K5_US] resize taps of the box's HR columns
+    K5Lerp* ly = lx + K5_US;                                        // [K5_US] ... rows
+    K5Box* boxes = reinterpret_cast<K5Box*>(ly + K5_US);            // [K5_CHUNK]
     BackXf* xfs = reinterpret_cast<BackXf*>(boxes + K5_CHUNK);      // [K5_CHUNK]
 
     const int b = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -406,7 +409,8 @@ k_backproject_tiled(const float* __restrict__ copies, const BackXf* __restrict__
                 const int ncx = bx.ncxy & 0xff, ncy = (bx.ncxy >> 8) & 0xff;
                 const int nux = 4 * ncx + 1, nuy = 4 * ncy + 1;           // U extent: HR positions 4*cb0 ... 4*cb0 + 4*nc
                 const float* yk = copies + ((size_t)b * N + k0 + kc) * h * w;
-                // ---- tap tables of the translate (source validity and the canvas of Z folded in) + T ---------
+                // ---- per-column / per-row tables: translate taps (source validity and the canvas of Z folded in)
+                //      and the resize taps of every HR column / row of the box --------------------------------
                 if (tid < 2 * K5_ZS) {
                     const bool col = tid < K5_ZS;
                     const int e = col ? tid : tid - K5_ZS;
@@ -415,46 +419,61 @@ k_backproject_tiled(const float* __restrict__ copies, const BackXf* __restrict__
                     float2 wv = make_float2(0.0f, 0.0f);
                     if (q >= 0 && q < lim) wv = warp_taps(q, t, (int)floorf(t), lim, ASR_INTERP_BILINEAR);
                     (col ? colw : roww)[e] = wv;
+                } else if (tid < 2 * K5_ZS + 2 * K5_US) {
+                    const int e2 = tid - 2 * K5_ZS;
+                    const bool col = e2 < K5_US;
+                    const int e = col ? e2 : e2 - K5_US;
+                    const int m = 4 * (col ? bx.cbx0 : bx.cby0) + e, lim = col ? W : H, n = col ? w : h;
+                    const float sc = (float)n / (float)lim;
+                    const float in = fsub(fmul(fadd((float)m, 0.5f), sc), 0.5f);
+                    const float f = floorf(in);
+                    K5Lerp L;
+                    L.i0 = max((int)f, 0); L.i1 = min((int)ceilf(in), n - 1); L.l = fsub(in, f);
+                    L.ok = (m >= 0 && m < lim && e < (col ? nux : nuy)) ? 1 : 0;
+                    if (!L.ok) { L.i0 = 0; L.i1 = 0; }
+                    (col ? lx : ly)[e] = L;
                 }
-                const float xs = (float)w / (float)W, ys = (float)h / (float)H;
-                for (int e = tid; e < (ncy + 2) * nux; e += K5_THREADS) {
-                    const int ry = e / nux, ex = e - ry * nux;
-                    const int lr = bx.cby0 - 1 + ry, mx = 4 * bx.cbx0 + ex;
-                    float tv = 0.0f;
-                    if (lr >= 0 && lr < h && mx >= 0 && mx < W) {
-                        const float in_x = fsub(fmul(fadd((float)mx, 0.5f), xs), 0.5f);
-                        const float fx = floorf(in_x);
-                        const int x0 = max((int)fx, 0), x1 = min((int)ceilf(in_x), w - 1);
-                        const float xl = fsub(in_x, fx);
-                        const float tl = __ldg(yk + lr * w + x0), tr = __ldg(yk + lr * w + x1);
-                        tv = fadd(tl, fmul(fsub(tr, tl), xl));
+                __syncthreads();
+                // ---- T = x-lerp of the LR rows the box touches ------------------------------------------------
+                for (int ry = warp; ry < ncy + 2; ry += K5_THREADS / 32) {
+                    const int lr = bx.cby0 - 1 + ry;
+                    const bool row_ok = lr >= 0 && lr < h;
+                    const float* yr = yk + (row_ok ? lr : 0) * w;
+                    for (int ex = lane; ex < nux; ex += 32) {
+                        const K5Lerp L = lx[ex];
+                        float tv = 0.0f;
+                        if (row_ok && L.ok) {
+                            const float tl = __ldg(yr + L.i0), tr = __ldg(yr + L.i1);
+                            tv = fadd(tl, fmul(fsub(tr, tl), L.l));
+                        }
+                        Tt[ry * K5_US + ex] = tv;
                     }
-                    Tt[ry * K5_US + ex] = tv;
                 }
                 __syncthreads();
                 // ---- U = upsampled image on the box ---------------------------------------------------------
-                for (int e = tid; e < nuy * nux; e += K5_THREADS) {
-                    const int ey = e / nux, ex = e - ey * nux;
-                    const int my = 4 * bx.cby0 + ey, mx = 4 * bx.cbx0 + ex;
-                    float uv = 0.0f;
-                    if (my >= 0 && my < H && mx >= 0 && mx < W) {
-                        const float in_y = fsub(fmul(fadd((float)my, 0.5f), ys), 0.5f);
-                        const float fy = floorf(in_y);
-                        const int y0 = max((int)fy, 0), y1 = min((int)ceilf(in_y), h - 1);
-                        const float yl = fsub(in_y, fy);
-                        const float t = Tt[(y0 - bx.cby0 + 1) * K5_US + ex], bb = Tt[(y1 - bx.cby0 + 1) * K5_US + ex];
-                        uv = fadd(t, fmul(fsub(bb, t), yl));
+                for (int ey = warp; ey < nuy; ey += K5_THREADS / 32) {
+                    const K5Lerp L = ly[ey];
+                    const float* t0 = Tt + (L.i0 - bx.cby0 + 1) * K5_US;
+                    const float* t1 = Tt + (L.i1 - bx.cby0 + 1) * K5_US;
+                    for (int ex = lane; ex < nux; ex += 32) {
+                        float uv = 0.0f;
+                        if (L.ok && lx[ex].ok) {
+                            const float t = t0[ex], bb = t1[ex];
+                            uv = fadd(t, fmul(fsub(bb, t), L.l));
+                        }
+                        Ut[ey * K5_US + ex] = uv;
                     }
-                    Ut[ey * K5_US + ex] = uv;
                 }
                 __syncthreads();
                 // ---- Z = translate(U) on the box ------------------------------------------------------------
                 const int nzx = 4 * ncx;
-                for (int e = tid; e < 4 * ncy * nzx; e += K5_THREADS) {
-                    const int ey = e / nzx, ex = e - ey * nzx;
-                    const float2 wc = colw[ex], wr = roww[ey];
-                    const float* u0 = Ut + ey * K5_US + ex;
-                    Zt[ey * K5_ZS + ex] = bilerp(u0[0], u0[1], u0[K5_US], u0[K5_US + 1], wc.x, wc.y, wr.x, wr.y);
+                for (int ey = warp; ey < 4 * ncy; ey += K5_THREADS / 32) {
+                    const float2 wr = roww[ey];
+                    for (int ex = lane; ex < nzx; ex += 32) {
+                        const float2 wc = colw[ex];
+                        const float* u0 = Ut + ey * K5_US + ex;
+                        Zt[ey * K5_ZS + ex] = bilerp(u0[0], u0[1], u0[K5_US], u0[K5_US + 1], wc.x, wc.y, wr.x, wr.y);
+                    }
                 }
                 __syncthreads();
                 // ---- rotate gather (packed fp32: the two lanes are columns lane, lane+32) ----------------------
