@@ -477,10 +477,9 @@ k_backproject_tiled(const float* __restrict__ copies, const BackXf* __restrict__
                 }
                 __syncthreads();
                 // ---- rotate gather (packed fp32: the two lanes are columns lane, lane+32) ----------------------
-                const char* zb = reinterpret_cast<const char*>(Zt);
                 const f32x2 r2p = pk(T.r2, T.r2), r5p = pk(T.r5, T.r5);
                 const f32x2 axp = pk(fmul(T.r0, X0f), fmul(T.r0, X1f)), ayp = pk(fmul(T.r3, X0f), fmul(T.r3, X1f));
-                unsigned cst = bx.cst;
+                unsigned cst = bx.cst + smem_u32(Zt);
                 asm volatile("" : "+r"(cst));
 #pragma unroll
                 for (int r = 0; r < 4; ++r) {
@@ -494,10 +493,11 @@ k_backproject_tiled(const float* __restrict__ copies, const BackXf* __restrict__
                     // the tap x_floor = -1, which lies outside the canvas and is an exact zero of Z
                     const f32x2 wx1 = sub2(ix, fxf), wx0 = sub2(one2, wx1);
                     const f32x2 wy1 = sub2(iy, fyf), wy0 = sub2(one2, wy1);
-                    const float* ta = reinterpret_cast<const float*>(zb + tap_offset<K5_ZS>(__float_as_uint(pk_lo(txx)), __float_as_uint(pk_lo(tyy)), cst));
-                    const float* tb = reinterpret_cast<const float*>(zb + tap_offset<K5_ZS>(__float_as_uint(pk_hi(txx)), __float_as_uint(pk_hi(tyy)), cst));
-                    v[r] = bilerp2(pk(ta[0], tb[0]), pk(ta[1], tb[1]), pk(ta[K5_ZS], tb[K5_ZS]), pk(ta[K5_ZS + 1], tb[K5_ZS + 1]),
-                                   wx0, wx1, wy0, wy1);
+                    const unsigned ta = tap_offset<K5_ZS>(__float_as_uint(pk_lo(txx)), __float_as_uint(pk_lo(tyy)), cst);
+                    const unsigned tb = tap_offset<K5_ZS>(__float_as_uint(pk_hi(txx)), __float_as_uint(pk_hi(tyy)), cst);
+                    v[r] = bilerp2(pk(lds_tap<0>(ta), lds_tap<0>(tb)), pk(lds_tap<4>(ta), lds_tap<4>(tb)),
+                                   pk(lds_tap<4 * K5_ZS>(ta), lds_tap<4 * K5_ZS>(tb)),
+                                   pk(lds_tap<4 * K5_ZS + 4>(ta), lds_tap<4 * K5_ZS + 4>(tb)), wx0, wx1, wy0, wy1);
                 }
             }
 #pragma unroll

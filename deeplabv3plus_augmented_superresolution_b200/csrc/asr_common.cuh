@@ -103,18 +103,24 @@ __device__ __forceinline__ f32x2 bilerp2(f32x2 v00, f32x2 v01, f32x2 v10, f32x2 
     return pk(fadd(pk_lo(n0), pk_lo(n1)), fadd(pk_hi(n0), pk_hi(n1)));
 }
 
-// byte offset 4*(raw_y*STRIDE + raw_x) + cst4 for STRIDE = 96, as three shift-adds (ALU pipe, the FMA
-// pipes carry nothing but the packed arithmetic)
+// shared-memory address of tap (y0,x0): 4*(raw_y*STRIDE + raw_x) + cst4, where cst4 folds the magic bias of the
+// raw floor bits, the box origin and the 32-bit shared address of the tile (mod 2^32).  One shift-add + one
+// multiply-add per pixel; the four taps are then immediate offsets of one register.
 template <int STRIDE>
 __device__ __forceinline__ unsigned tap_offset(unsigned raw_x, unsigned raw_y, unsigned cst4) {
-    static_assert(STRIDE == 96, "stride 96 = 64 + 32");
     unsigned o;
     asm("{\n.reg .u32 t;\n"
-        "shl.b32 t, %1, 2;\n add.u32 %0, t, %3;\n"
-        "shl.b32 t, %2, 7;\n add.u32 %0, %0, t;\n"
-        "shl.b32 t, %2, 8;\n add.u32 %0, %0, t;\n}"
-        : "=r"(o) : "r"(raw_x), "r"(raw_y), "r"(cst4));
+        "shl.b32 t, %1, 2;\n add.u32 t, t, %3;\n"
+        "mad.lo.u32 %0, %2, %4, t;\n}"
+        : "=r"(o) : "r"(raw_x), "r"(raw_y), "r"(cst4), "n"(4 * STRIDE));
     return o;
+}
+// ld.shared of one tap: 32-bit shared address + immediate byte offset
+template <int OFF>
+__device__ __forceinline__ float lds_tap(unsigned addr) {
+    float v;
+    asm("ld.shared.f32 %0, [%1 + %2];" : "=f"(v) : "r"(addr), "n"(OFF));
+    return v;
 }
 
 __device__ __forceinline__ float sgn(float v) { return (v > 0.0f) ? 1.0f : ((v < 0.0f) ? -1.0f : 0.0f); }

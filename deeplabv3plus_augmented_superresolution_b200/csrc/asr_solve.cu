@@ -184,9 +184,8 @@ k_forward_residual(const __grid_constant__ CUtensorMap xmap, const float* __rest
         const float ax = fmul(T.r0, qxf), ay = fmul(T.r3, qxf);
         // byte offset of tap (y0,x0) = 4*(raw_y*XS + raw_x + cst) (mod 2^32); kept opaque so that the compiler
         // cannot split the magic constant out of it and re-add it once per tap
-        unsigned cst = (0u - (unsigned)(kMagicBits + boxs[1]) * K1_XS - (unsigned)(kMagicBits + boxs[0])) << 2;
+        unsigned cst = ((0u - (unsigned)(kMagicBits + boxs[1]) * K1_XS - (unsigned)(kMagicBits + boxs[0])) << 2) + smem_u32(xt);
         asm volatile("" : "+r"(cst));
-        const char* xtb = reinterpret_cast<const char*>(xt);
         float* prow = pb + (9 * g) * K1_PBS + pcn;
         const f32x2 axp = pk(ax, ax), ayp = pk(ay, ay), r2p = pk(T.r2, T.r2), r5p = pk(T.r5, T.r5);
         const f32x2 magic2 = pk(kMagic, kMagic), one2 = pk(1.0f, 1.0f);
@@ -204,10 +203,11 @@ k_forward_residual(const __grid_constant__ CUtensorMap xmap, const float* __rest
             // multiplies the out-of-image tap x_floor = -1, i.e. an exact zero
             const f32x2 wx1 = sub2(ix, fxf), wx0 = sub2(one2, wx1);
             const f32x2 wy1 = sub2(iy, fyf), wy0 = sub2(one2, wy1);
-            const float* ta = reinterpret_cast<const float*>(xtb + tap_offset<K1_XS>(__float_as_uint(pk_lo(tx)), __float_as_uint(pk_lo(ty)), cst));
-            const float* tb = reinterpret_cast<const float*>(xtb + tap_offset<K1_XS>(__float_as_uint(pk_hi(tx)), __float_as_uint(pk_hi(ty)), cst));
-            const f32x2 o = bilerp2(pk(ta[0], tb[0]), pk(ta[1], tb[1]), pk(ta[K1_XS], tb[K1_XS]), pk(ta[K1_XS + 1], tb[K1_XS + 1]),
-                                    wx0, wx1, wy0, wy1);
+            const unsigned ta = tap_offset<K1_XS>(__float_as_uint(pk_lo(tx)), __float_as_uint(pk_lo(ty)), cst);
+            const unsigned tb = tap_offset<K1_XS>(__float_as_uint(pk_hi(tx)), __float_as_uint(pk_hi(ty)), cst);
+            const f32x2 o = bilerp2(pk(lds_tap<0>(ta), lds_tap<0>(tb)), pk(lds_tap<4>(ta), lds_tap<4>(tb)),
+                                    pk(lds_tap<4 * K1_XS>(ta), lds_tap<4 * K1_XS>(tb)),
+                                    pk(lds_tap<4 * K1_XS + 4>(ta), lds_tap<4 * K1_XS + 4>(tb)), wx0, wx1, wy0, wy1);
             prow[m * K1_PBS] = pk_lo(o);
             prow[(m + 1) * K1_PBS] = pk_hi(o);
         }
@@ -216,8 +216,8 @@ k_forward_residual(const __grid_constant__ CUtensorMap xmap, const float* __rest
             const Floor fx = floor_magic(ix), fy = floor_magic(iy);
             const float wx1 = fsub(ix, fx.f), wx0 = fsub(1.0f, wx1);
             const float wy1 = fsub(iy, fy.f), wy0 = fsub(1.0f, wy1);
-            const float* t0 = reinterpret_cast<const float*>(xtb + tap_offset<K1_XS>((unsigned)fx.raw, (unsigned)fy.raw, cst));
-            prow[8 * K1_PBS] = bilerp(t0[0], t0[1], t0[K1_XS], t0[K1_XS + 1], wx0, wx1, wy0, wy1);
+            const unsigned t0 = tap_offset<K1_XS>((unsigned)fx.raw, (unsigned)fy.raw, cst);
+            prow[8 * K1_PBS] = bilerp(lds_tap<0>(t0), lds_tap<4>(t0), lds_tap<4 * K1_XS>(t0), lds_tap<4 * K1_XS + 4>(t0), wx0, wx1, wy0, wy1);
         }
     }
     __syncthreads();
@@ -422,9 +422,8 @@ k_gradient_update(const __grid_constant__ CUtensorMap rmap, const float* __restr
                 if (!(bx.ncxy >> 16)) {
                     const InvXf T = xfs[kc];
                     // byte offset of tap (y0,x0) = 4*(raw_y*US + raw_x + cst) (mod 2^32)
-                    unsigned cst = (bx.cst + (unsigned)((kc & 1) * (K2_US * K2_UR))) << 2;
-                    asm volatile("" : "+r"(cst));
-                    const char* utb = reinterpret_cast<const char*>(ut);
+                    unsigned cst = ((bx.cst + (unsigned)((kc & 1) * (K2_US * K2_UR))) << 2) + smem_u32(ut);
+                    asm volatile("" : "+r"(cst));   // opaque and ordered after the wait above: no tap load can be hoisted over it
                     const f32x2 b2p = pk(T.b2, T.b2), b5p = pk(T.b5, T.b5);
                     // products stay scalar (a packed product feeding a packed sum would be contracted, asr_common.cuh)
                     const f32x2 axp = pk(fmul(T.b0, X0f), fmul(T.b0, X1f)), ayp = pk(fmul(T.b3, X0f), fmul(T.b3, X1f));
@@ -441,12 +440,11 @@ k_gradient_update(const __grid_constant__ CUtensorMap rmap, const float* __restr
                         // multiplies the tap x_floor = -1, which lies outside the canvas and is an exact zero of u
                         const f32x2 wx1 = sub2(ix, fxf), wx0 = sub2(one2, wx1);
                         const f32x2 wy1 = sub2(iy, fyf), wy0 = sub2(one2, wy1);
-                        const unsigned oa = tap_offset<K2_US>(__float_as_uint(pk_lo(tx)), __float_as_uint(pk_lo(ty)), cst);
-                        const unsigned ob = tap_offset<K2_US>(__float_as_uint(pk_hi(tx)), __float_as_uint(pk_hi(ty)), cst);
-                        const float* ta = reinterpret_cast<const float*>(utb + oa);
-                        const float* tb = reinterpret_cast<const float*>(utb + ob);
-                        accp[r] = add2(accp[r], bilerp2(pk(ta[0], tb[0]), pk(ta[1], tb[1]), pk(ta[K2_US], tb[K2_US]),
-                                                        pk(ta[K2_US + 1], tb[K2_US + 1]), wx0, wx1, wy0, wy1));
+                        const unsigned ta = tap_offset<K2_US>(__float_as_uint(pk_lo(tx)), __float_as_uint(pk_lo(ty)), cst);
+                        const unsigned tb = tap_offset<K2_US>(__float_as_uint(pk_hi(tx)), __float_as_uint(pk_hi(ty)), cst);
+                        accp[r] = add2(accp[r], bilerp2(pk(lds_tap<0>(ta), lds_tap<0>(tb)), pk(lds_tap<4>(ta), lds_tap<4>(tb)),
+                                                        pk(lds_tap<4 * K2_US>(ta), lds_tap<4 * K2_US>(tb)),
+                                                        pk(lds_tap<4 * K2_US + 4>(ta), lds_tap<4 * K2_US + 4>(tb)), wx0, wx1, wy0, wy1));
                     }
                 }
                 // hand the buffer back; the last two hand-backs of a chunk have no taker
