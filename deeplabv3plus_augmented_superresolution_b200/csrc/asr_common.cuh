@@ -119,7 +119,8 @@ __device__ __forceinline__ unsigned tap_offset(unsigned raw_x, unsigned raw_y, u
 template <int OFF>
 __device__ __forceinline__ float lds_tap(unsigned addr) {
     float v;
-    asm("ld.shared.f32 %0, [%1 + %2];" : "=f"(v) : "r"(addr), "n"(OFF));
+    // volatile: keeps the load between the barrier operations (also volatile asm) that hand the tile over
+    asm volatile("ld.shared.f32 %0, [%1 + %2];" : "=f"(v) : "r"(addr), "n"(OFF));
     return v;
 }
 
