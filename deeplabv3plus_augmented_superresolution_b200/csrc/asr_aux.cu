@@ -64,9 +64,25 @@ __global__ void k_pad_channels(const float* __restrict__ img, float4* __restrict
     }
 }
 
-__device__ __forceinline__ float4 bilerp4(float4 a, float4 b, float4 c, float4 d, float wx0, float wx1, float wy0, float wy1) {
-    return make_float4(bilerp(a.x, b.x, c.x, d.x, wx0, wx1, wy0, wy1), bilerp(a.y, b.y, c.y, d.y, wx0, wx1, wy0, wy1),
-                       bilerp(a.z, b.z, c.z, d.z, wx0, wx1, wy0, wy1), bilerp(a.w, b.w, c.w, d.w, wx0, wx1, wy0, wy1));
+// bilinear_interpolation() of the op on the C live channels of four padded pixels: channel pairs travel as the two
+// lanes of packed fp32 instructions with the weights broadcast (asr_common.cuh: products packed, sums scalar)
+template <int C>
+__device__ __forceinline__ float4 bilerpC(float4 a, float4 b, float4 c, float4 d, float wx0, float wx1, float wy0, float wy1) {
+    float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+    const f32x2 x0 = pk(wx0, wx0), x1 = pk(wx1, wx1), y0 = pk(wy0, wy0), y1 = pk(wy1, wy1);
+    if (C >= 2) {
+        const f32x2 r = bilerp2(pk(a.x, a.y), pk(b.x, b.y), pk(c.x, c.y), pk(d.x, d.y), x0, x1, y0, y1);
+        o.x = pk_lo(r); o.y = pk_hi(r);
+    } else {
+        o.x = bilerp(a.x, b.x, c.x, d.x, wx0, wx1, wy0, wy1);
+    }
+    if (C == 4) {
+        const f32x2 r = bilerp2(pk(a.z, a.w), pk(b.z, b.w), pk(c.z, c.w), pk(d.z, d.w), x0, x1, y0, y1);
+        o.z = pk_lo(r); o.w = pk_hi(r);
+    } else if (C == 3) {
+        o.z = bilerp(a.z, b.z, c.z, d.z, wx0, wx1, wy0, wy1);
+    }
+    return o;
 }
 
 template <int C>
@@ -93,10 +109,13 @@ k_warp_affine(const float4* __restrict__ img, const WarpXf* __restrict__ xf, flo
         const float ix = affine_coord(T.r0, qx, T.r1, qy, T.r2), iy = affine_coord(T.r3, qx, T.r4, qy, T.r5);
         float4 v;
         if (interp == ASR_INTERP_BILINEAR) {
-            const float fx = floorf(ix), fy = floorf(iy);
-            const float wx0 = fsub(fadd(fx, 1.0f), ix), wx1 = fsub(ix, fx);
-            const float wy0 = fsub(fadd(fy, 1.0f), iy), wy1 = fsub(iy, fy);
-            const int x0 = (int)fx, y0 = (int)fy;
+            // floor of both coordinates with the magic-number add (asr_common.cuh), x and y as the two packed lanes
+            const f32x2 ixy = pk(ix, iy), magic2 = pk(kMagic, kMagic);
+            const f32x2 raw = add2_rd(ixy, magic2);
+            const f32x2 fl2 = sub2(raw, magic2);
+            const f32x2 w1 = sub2(ixy, fl2), w0 = sub2(add2(fl2, pk(1.0f, 1.0f)), ixy);   // (floor + 1) - v, v - floor
+            const float wx0 = pk_lo(w0), wx1 = pk_lo(w1), wy0 = pk_hi(w0), wy1 = pk_hi(w1);
+            const int x0 = (int)__float_as_uint(pk_lo(raw)) - kMagicBits, y0 = (int)__float_as_uint(pk_hi(raw)) - kMagicBits;
             const bool vx0 = x0 >= 0 && x0 < W, vx1 = x0 + 1 >= 0 && x0 + 1 < W;
             const bool vy0 = y0 >= 0 && y0 < H, vy1 = y0 + 1 >= 0 && y0 + 1 < H;
             const float4* b00 = img + ((ptrdiff_t)y0 * W + x0);
@@ -104,7 +123,7 @@ k_warp_affine(const float4* __restrict__ img, const WarpXf* __restrict__ xf, flo
             const float4 v01 = (vy0 && vx1) ? __ldg(b00 + 1) : zero4;
             const float4 v10 = (vy1 && vx0) ? __ldg(b00 + W) : zero4;
             const float4 v11 = (vy1 && vx1) ? __ldg(b00 + W + 1) : zero4;
-            v = bilerp4(v00, v01, v10, v11, wx0, wx1, wy0, wy1);
+            v = bilerpC<C>(v00, v01, v10, v11, wx0, wx1, wy0, wy1);
         } else {
             const long xn = (long)roundf(ix), yn = (long)roundf(iy);
             v = (xn >= 0 && xn < W && yn >= 0 && yn < H) ? __ldg(img + ((size_t)yn * W + xn)) : zero4;
@@ -121,7 +140,7 @@ k_warp_affine(const float4* __restrict__ img, const WarpXf* __restrict__ xf, flo
         const float4 a = p[ty * K3_P + tx], b = p[ty * K3_P + tx + 1], c = p[(ty + 1) * K3_P + tx], d = p[(ty + 1) * K3_P + tx + 1];
         float4 v;
         if (interp == ASR_INTERP_BILINEAR) {
-            v = bilerp4(a, b, c, d, wc.x, wc.y, wr.x, wr.y);
+            v = bilerpC<C>(a, b, c, d, wc.x, wc.y, wr.x, wr.y);
         } else {   // exactly one tap has weight 1 (or none: zero fill)
             const float4 top = (wc.x != 0.0f) ? a : ((wc.y != 0.0f) ? b : zero4);
             const float4 bot = (wc.x != 0.0f) ? c : ((wc.y != 0.0f) ? d : zero4);
@@ -573,6 +592,7 @@ extern "C" int asr_warp_affine(const float* d_image, const float* h_angles, cons
     if (!d_image || !h_angles || !h_shifts || !d_out) return fail(ASR_ENULL, "null argument");
     if (N <= 0 || H <= 0 || W <= 0 || C <= 0 || C > K3_CMAX) return fail(ASR_EINVAL, "need N,H,W > 0 and 1 <= C <= %d", K3_CMAX);
     if (N > 65535) return fail(ASR_EINVAL, "N must be <= 65535");
+    if (H > (1 << 20) || W > (1 << 20)) return fail(ASR_EINVAL, "image too large for the fp32 floor trick");
     if (interp != ASR_INTERP_NEAREST && interp != ASR_INTERP_BILINEAR) return fail(ASR_EINVAL, "unknown interpolation %d", interp);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     std::vector<WarpXf> xf(N);
