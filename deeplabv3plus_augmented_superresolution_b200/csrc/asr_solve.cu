@@ -86,12 +86,15 @@ constexpr int K1_PC = 3 * K1_TJ;       // needed p columns (48) and rows (36) pe
 constexpr int K1_PR = 3 * K1_TI;
 constexpr int K1_PBS = K1_PC + 1;      // p buffer stride
 constexpr int K1_RPS = 10;             // row-product table stride per row group (9 rows, padded to keep pairs 8-byte aligned)
-constexpr int K1_XS = 96;              // TMA box width  (floats): 62*sqrt(2)+2+3 < 96, multiple of 32 -> conflict-free gathers
+constexpr int K1_XS_BIG = 96;          // TMA box width (floats) for any rotation: 62*sqrt(2)+2+3 < 96
+constexpr int K1_XS_SMALL = 96;        // a narrower box (80: pitch 16 mod 32) saves TMA bytes but adds conflicts across source rows: 29.5 vs 28.0 us
 constexpr int K1_XR_SMALL = 60;        // TMA box height when 62|sin|+46|cos|+3 <= 60 for every copy (|angle| <~ 0.19 rad): 7 CTAs/SM
 constexpr int K1_XR_BIG = 84;          // ... for any rotation: sqrt(62^2+46^2)+3 < 84: 5 CTAs/SM
 template <int XR>
+constexpr int k1_xs() { return XR == K1_XR_SMALL ? K1_XS_SMALL : K1_XS_BIG; }
+template <int XR>
 constexpr size_t k1_smem() {
-    return sizeof(float) * K1_XS * XR + sizeof(float) * (K1_PR * K1_PBS) + sizeof(float4) * (K1_TJ + K1_TI) + sizeof(float) * 2 * 4 * K1_RPS + 16;
+    return sizeof(float) * k1_xs<XR>() * XR + sizeof(float) * (K1_PR * K1_PBS) + sizeof(float4) * (K1_TJ + K1_TI) + sizeof(float) * 2 * 4 * K1_RPS + 16;
 }
 
 // translate stencil weights of z-column Z on the window (Z+s, Z+s+1), validity of p folded in
@@ -117,6 +120,7 @@ k_forward_residual(const __grid_constant__ CUtensorMap xmap, const float* __rest
     const ImgParams P = ip[b];
     if (ks >= P.n_kept || it >= P.num_iter) return;
 
+    constexpr int K1_XS = (XR == K1_XR_SMALL) ? K1_XS_SMALL : K1_XS_BIG;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ __align__(8) unsigned long long bar;
     float* xt = reinterpret_cast<float*>(smem_raw);                              // [XR][K1_XS], filled by TMA
@@ -146,8 +150,10 @@ k_forward_residual(const __grid_constant__ CUtensorMap xmap, const float* __rest
         // TMA needs the innermost start coordinate 16-byte aligned (an unaligned start faults with
         // "illegal instruction" on B200: scripts/dev/tma_test3.cu), so the box starts at bx0 rounded down to 4
         const int bx0a = bx0 & ~3;
-        // empty: the rotated image is all zero here (a box beyond the buffer cannot happen for a rotation)
-        const int empty = (bx1 < 0 || bx0 >= W || by1 < 0 || by0 >= H || bx1 - bx0a >= K1_XS || by1 - by0 >= XR);
+        // empty: the rotated image is all zero here
+        const int empty = (bx1 < 0 || bx0 >= W || by1 < 0 || by0 >= H);
+        // the host picks the box variant from the same transforms (build_tables): a box that does not fit is a bug, not data
+        if (!empty && (bx1 - bx0a >= K1_XS || by1 - by0 >= XR)) __trap();
         if (lane == 0) {
             boxs[0] = bx0a; boxs[1] = by0; boxs[2] = empty;
             mbar_init(&bar, 1);
@@ -782,6 +788,8 @@ static void build_tables(const AsrSolveParams* params, int n_params, const float
             T.fwd[o] = FwdXf{rot[0], rot[1], rot[2], rot[3], rot[4], rot[5], tr[2], tr[5]};
             // K1 box rows <= 62|t3| + 46|t4| + 3 (corner span of the 63x47 p region, the +1 tap, floor); small margin
             if (62.0f * fabsf(rot[3]) + 46.0f * fabsf(rot[4]) + 3.05f > (float)K1_XR_SMALL) T.small_box = false;
+            // ... and columns <= 62|t0| + 46|t1| + 3, plus up to 3 for the 16-byte aligned start
+            if (62.0f * fabsf(rot[0]) + 46.0f * fabsf(rot[1]) + 6.05f > (float)K1_XS_SMALL) T.small_box = false;
             T.inv[o] = InvXf{roti[0], roti[1], roti[2], roti[3], roti[4], roti[5], tri[2], tri[5]};
             T.src[o] = k;
             ++kept;
@@ -867,7 +875,7 @@ static int make_x_map(CUtensorMap* map, const float* base, int B, int H, int W, 
     }
     const cuuint64_t gdim[3] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
     const cuuint64_t gstride[2] = {(cuuint64_t)W * sizeof(float), (cuuint64_t)W * H * sizeof(float)};
-    const cuuint32_t box[3] = {K1_XS, (cuuint32_t)box_rows, 1};
+    const cuuint32_t box[3] = {(cuuint32_t)(box_rows == K1_XR_SMALL ? K1_XS_SMALL : K1_XS_BIG), (cuuint32_t)box_rows, 1};
     const cuuint32_t estr[3] = {1, 1, 1};
     const CUresult r = encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), gdim, gstride, box, estr,
                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
