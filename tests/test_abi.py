@@ -79,6 +79,20 @@ def test_aux_entry_points_validate_arguments(L):
     assert L.asr_minmax_normalize(fake, 0, 0.0, 1.0, fake, fake, None) == -1
 
 
+def test_plain_c_consumer(L, tmp_path):
+    """include/asr.h compiles as C99 and a C program links and calls the library (no Python, no torch, no GPU)."""
+    import subprocess
+    exe = str(tmp_path / "abi_consumer")
+    libdir = os.path.dirname(_lib.LIB_PATH)
+    env = dict(os.environ); env.pop("CC", None)
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "tests", "c", "abi_consumer.c"), "-o", exe, "-L", libdir, "-lasr",
+                           "-Wl,-rpath," + libdir], env=env)
+    out = subprocess.run([exe], capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert "c abi ok" in out.stdout
+
+
 def test_missing_library_fails_loudly(monkeypatch, tmp_path):
     monkeypatch.setattr(_lib, "_lib", None)
     monkeypatch.setattr(_lib, "LIB_PATH", str(tmp_path / "libasr.so"))
