@@ -6,8 +6,10 @@
 //   tape.gradient (:126-133): ResizeBilinearGrad -> warp-grad(translate) -> warp-grad(rotate) -> sum over copies
 //   optimizer.apply_gradients (:134-135, optimizer.py:21-41)
 // with two kernels per iteration for a whole batch of images:
-//   k_forward_residual   r_k = D T_k R_k x - y_k              (one CTA per 16x16 LR tile per copy)
-//   k_gradient_update    x' = opt(x, sum_k W_k^grad r_k + reg) (one CTA per 64x64 HR tile, loops copies)
+//   k_forward_residual   r_k = D T_k R_k x - y_k              (one CTA per 16x12 LR tile per copy, TMA-staged x box)
+//   k_gradient_update    x' = opt(x, sum_k W_k^grad r_k + reg) (one CTA per 64x64 HR tile loops over the copies:
+//                                                               8 gather warps + 4 TMA-fed fill warps)
+// plus k_tap_tables once per solve.  The gathers run on packed fp32 (FADD2/FMUL2, two pixels per instruction).
 // Both are gather-form (no atomics) and bit-reproduce the un-fused fp32 evaluation order of the
 // TensorFlow ops (see asr_common.cuh).  DESIGN.md derives the restructurings used here and why
 // each is bit-identical to the literal two-pass evaluation.
@@ -73,10 +75,10 @@ __global__ void k_init_upsample(const float* __restrict__ copies, const ImgParam
 // For copy k and LR cell (i,j):  r = resize(translate(rotate(x)))[i,j] - y_k[i,j].
 // The resize reads only z at rows {4i+1,4i+2} x cols {4j+1,4j+2}; each z is a 2x2 stencil of the
 // rotated image p on integer positions, so one cell needs p on a 3x3 patch whose origin is
-// (4j+1+floor(-dx), 4i+1+floor(-dy)).  A CTA (16x16 cells, one copy) bounds the x region those
+// (4j+1+floor(-dx), 4i+1+floor(-dy)).  A CTA (16x12 cells, one copy) bounds the x region those
 // patches can touch from the four corner coordinates, pulls that box into shared memory with ONE
 // TMA tensor load (cp.async.bulk.tensor; out-of-image elements arrive as zeros, which is exactly the
-// op's fill), evaluates the 48x48 needed p values with the op's arithmetic, and a second phase
+// op's fill), evaluates the 48x36 needed p values with the op's arithmetic, and a second phase
 // combines them per cell with per-column/row tap tables that carry the literal translate weights,
 // the zero fill of p outside the canvas, and the rounding case floor(fl(Z-dx)) == Z+floor(-dx)+1.
 constexpr int K1_TJ = 16;              // LR tile: 16 cells wide ...
@@ -86,15 +88,13 @@ constexpr int K1_PC = 3 * K1_TJ;       // needed p columns (48) and rows (36) pe
 constexpr int K1_PR = 3 * K1_TI;
 constexpr int K1_PBS = K1_PC + 1;      // p buffer stride
 constexpr int K1_RPS = 10;             // row-product table stride per row group (9 rows, padded to keep pairs 8-byte aligned)
-constexpr int K1_XS_BIG = 96;          // TMA box width (floats) for any rotation: 62*sqrt(2)+2+3 < 96
-constexpr int K1_XS_SMALL = 96;        // a narrower box (80: pitch 16 mod 32) saves TMA bytes but adds conflicts across source rows: 29.5 vs 28.0 us
+constexpr int K1_XS = 96;              // TMA box width (floats): 62*sqrt(2)+2+3 < 96, multiple of 32 (a pitch of 80 = 16 mod 32 saves TMA
+                                       // bytes for small rotations but adds conflicts across source rows: measured 29.5 vs 28.0 us)
 constexpr int K1_XR_SMALL = 60;        // TMA box height when 62|sin|+46|cos|+3 <= 60 for every copy (|angle| <~ 0.19 rad): 7 CTAs/SM
 constexpr int K1_XR_BIG = 84;          // ... for any rotation: sqrt(62^2+46^2)+3 < 84: 5 CTAs/SM
 template <int XR>
-constexpr int k1_xs() { return XR == K1_XR_SMALL ? K1_XS_SMALL : K1_XS_BIG; }
-template <int XR>
 constexpr size_t k1_smem() {
-    return sizeof(float) * k1_xs<XR>() * XR + sizeof(float) * (K1_PR * K1_PBS) + sizeof(float4) * (K1_TJ + K1_TI) + sizeof(float) * 2 * 4 * K1_RPS + 16;
+    return sizeof(float) * K1_XS * XR + sizeof(float) * (K1_PR * K1_PBS) + sizeof(float4) * (K1_TJ + K1_TI) + sizeof(float) * 2 * 4 * K1_RPS + 16;
 }
 
 // translate stencil weights of z-column Z on the window (Z+s, Z+s+1), validity of p folded in
@@ -120,7 +120,6 @@ k_forward_residual(const __grid_constant__ CUtensorMap xmap, const float* __rest
     const ImgParams P = ip[b];
     if (ks >= P.n_kept || it >= P.num_iter) return;
 
-    constexpr int K1_XS = (XR == K1_XR_SMALL) ? K1_XS_SMALL : K1_XS_BIG;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ __align__(8) unsigned long long bar;
     float* xt = reinterpret_cast<float*>(smem_raw);                              // [XR][K1_XS], filled by TMA
@@ -788,8 +787,6 @@ static void build_tables(const AsrSolveParams* params, int n_params, const float
             T.fwd[o] = FwdXf{rot[0], rot[1], rot[2], rot[3], rot[4], rot[5], tr[2], tr[5]};
             // K1 box rows <= 62|t3| + 46|t4| + 3 (corner span of the 63x47 p region, the +1 tap, floor); small margin
             if (62.0f * fabsf(rot[3]) + 46.0f * fabsf(rot[4]) + 3.05f > (float)K1_XR_SMALL) T.small_box = false;
-            // ... and columns <= 62|t0| + 46|t1| + 3, plus up to 3 for the 16-byte aligned start
-            if (62.0f * fabsf(rot[0]) + 46.0f * fabsf(rot[1]) + 6.05f > (float)K1_XS_SMALL) T.small_box = false;
             T.inv[o] = InvXf{roti[0], roti[1], roti[2], roti[3], roti[4], roti[5], tri[2], tri[5]};
             T.src[o] = k;
             ++kept;
@@ -875,7 +872,7 @@ static int make_x_map(CUtensorMap* map, const float* base, int B, int H, int W, 
     }
     const cuuint64_t gdim[3] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
     const cuuint64_t gstride[2] = {(cuuint64_t)W * sizeof(float), (cuuint64_t)W * H * sizeof(float)};
-    const cuuint32_t box[3] = {(cuuint32_t)(box_rows == K1_XR_SMALL ? K1_XS_SMALL : K1_XS_BIG), (cuuint32_t)box_rows, 1};
+    const cuuint32_t box[3] = {K1_XS, (cuuint32_t)box_rows, 1};
     const cuuint32_t estr[3] = {1, 1, 1};
     const CUresult r = encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), gdim, gstride, box, estr,
                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
