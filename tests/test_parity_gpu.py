@@ -197,6 +197,20 @@ def test_full_size_batch_properties():
     assert torch.equal(x_perm, x[perm])
 
 
+def test_full_occupancy_determinism_and_parity():
+    """48 full-size images (3072 gradient CTAs, 422k forward CTAs per launch: every SM holds co-resident CTAs of the
+    warp-specialised kernel).  A race in the tile hand-off would show up as run-to-run differences or as a mismatch
+    against the oracle; both are checked bit for bit."""
+    copies, ang, sh = synth(48, 100, (128, 128), 0.15, 80, seed=97)
+    P = A.SolveParams(num_iter=6)
+    x1 = A.solve_batched(copies, ang, sh, P)
+    x2 = A.solve_batched(copies, ang, sh, P)
+    assert torch.equal(x1, x2)
+    for b in (0, 23, 47):
+        xo, _ = O.augmented_superresolution(copies[b].cpu().numpy(), ang[b], sh[b], O.SolveParams(num_iter=6), output_size=(512, 512))
+        np.testing.assert_array_equal(x1[b].cpu().numpy(), xo[..., 0])
+
+
 # --------------------------------------------------------------------------------------------------
 # warp, OPM, normalise, threshold, back-projection
 # --------------------------------------------------------------------------------------------------
