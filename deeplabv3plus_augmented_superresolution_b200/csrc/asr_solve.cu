@@ -15,6 +15,7 @@
 // each is bit-identical to the literal two-pass evaluation.
 #include <cuda.h>
 #include <math.h>
+#include <stdlib.h>
 #include <vector>
 
 #include "asr_common.cuh"
@@ -274,14 +275,14 @@ k_forward_residual(const __grid_constant__ CUtensorMap xmap, const float* __rest
 // overlaps the gather of copy k and the gather warps carry no bookkeeping at all.
 // Bounding boxes and the inverse transforms of a chunk of 128 copies are computed once into shared
 // memory (one thread per copy) before the roles split.
-constexpr int K2_T = 64;               // HR tile edge
-constexpr int K2_GW = 8;               // gather warps; thread owns pixels (lane + 32c, warp + 8r), c<2, r<8
+constexpr int K2_T = 64;               // HR tile width; the tile height TY is 64 for batches that fill the GPU and 32 for one or two images
+                                       // (one 512^2 image is only 64 tiles of 64x64: such a solve is latency-bound, 104 -> 79 us per iteration)
+constexpr int K2_GW = 8;               // gather warps; thread owns pixels (lane + 32c, warp + 8r), c<2, r<TY/8
 constexpr int K2_FW = 4;               // fill warps
-constexpr int K2_ROWS = K2_T / K2_GW;  // rows per gather thread
 constexpr int K2_NG = 32 * K2_GW, K2_NF = 32 * K2_FW;
 constexpr int K2_THREADS = K2_NG + K2_NF;
 constexpr int K2_US = 96;              // u tile stride: 64*sqrt(2)+2+3 < 96, multiple of 32
-constexpr int K2_UR = 96;              // u tile rows
+template <int TY> struct K2Rows { static constexpr int value = TY == 64 ? 96 : 80; };   // u tile rows: sqrt(63^2+(TY-1)^2)+2 -> cells
 constexpr int K2_CHUNK = 128;          // copies whose boxes/transforms are staged at once
 enum { BAR_EMPTY = 1 };   // named barriers 1,2 (0 is __syncthreads)
 struct __align__(16) KBox {
@@ -304,8 +305,11 @@ struct __align__(128) K2Stage {
     float4 rtap[K2_BC][2];             // same per cell row
 };
 constexpr unsigned K2_RBOX_BYTES = sizeof(float) * K2_BC * K2_RW, K2_TAP_BYTES = sizeof(float4) * K2_BC * 2;
-constexpr size_t K2_SMEM = sizeof(float) * 2 * K2_US * K2_UR + (sizeof(KBox) + sizeof(InvXf)) * K2_CHUNK + sizeof(K2Stage) * K2_STAGES +
-                           sizeof(float2) * 2 * K2_T;
+template <int TY>
+constexpr size_t k2_smem() {
+    return sizeof(float) * 2 * K2_US * K2Rows<TY>::value + (sizeof(KBox) + sizeof(InvXf)) * K2_CHUNK + sizeof(K2Stage) * K2_STAGES +
+           sizeof(float2) * 2 * TY;
+}
 
 __device__ __forceinline__ void bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 __device__ __forceinline__ void bar_arrive(int id, int n) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); }
@@ -340,7 +344,7 @@ __global__ void k_tap_tables(const InvXf* __restrict__ inv, float2* __restrict__
     }
 }
 
-template <bool WRITE_GRAD, bool BTV>
+template <bool WRITE_GRAD, bool BTV, int TY>
 __global__ void __launch_bounds__(K2_THREADS, 2)
 k_gradient_update(const __grid_constant__ CUtensorMap rmap, const float* __restrict__ x_cur, float* __restrict__ x_next,
                   float* __restrict__ s0, float* __restrict__ s1, float* __restrict__ s2, const float2* __restrict__ tapc,
@@ -350,17 +354,18 @@ k_gradient_update(const __grid_constant__ CUtensorMap rmap, const float* __restr
     const ImgParams P = ip[b];
     if (it >= P.num_iter) return;
 
+    constexpr int K2_UR = K2Rows<TY>::value, K2_ROWS = TY / K2_GW;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float* ut = reinterpret_cast<float*>(smem_raw);                       // [2][K2_UR][K2_US]
     K2Stage* stages = reinterpret_cast<K2Stage*>(ut + 2 * K2_US * K2_UR);  // [K2_STAGES]
     KBox* boxes = reinterpret_cast<KBox*>(stages + K2_STAGES);            // [K2_CHUNK]
     InvXf* xfs = reinterpret_cast<InvXf*>(boxes + K2_CHUNK);              // [K2_CHUNK]
-    float2* rowp = reinterpret_cast<float2*>(xfs + K2_CHUNK);             // [2][K2_T] (fl(b1*Y), fl(b4*Y)) of the tile's rows, per u buffer
+    float2* rowp = reinterpret_cast<float2*>(xfs + K2_CHUNK);             // [2][TY] (fl(b1*Y), fl(b4*Y)) of the tile's rows, per u buffer
     __shared__ __align__(8) unsigned long long stage_bar[K2_STAGES], full_bar[2];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int ntx = (W + K2_T - 1) / K2_T;
-    const int tx0 = (blockIdx.x % ntx) * K2_T, ty0 = (blockIdx.x / ntx) * K2_T;
+    const int tx0 = (blockIdx.x % ntx) * K2_T, ty0 = (blockIdx.x / ntx) * TY;
     const InvXf* invb = inv + (size_t)b * N;
     const int nk = P.n_kept;
     if (tid == 0) {
@@ -393,7 +398,7 @@ k_gradient_update(const __grid_constant__ CUtensorMap rmap, const float* __restr
             float xmin = INFINITY, xmax = -INFINITY, ymin = INFINITY, ymax = -INFINITY;
 #pragma unroll
             for (int cnr = 0; cnr < 4; ++cnr) {
-                const float X = (float)(tx0 + ((cnr & 1) ? K2_T - 1 : 0)), Y = (float)(ty0 + ((cnr & 2) ? K2_T - 1 : 0));
+                const float X = (float)(tx0 + ((cnr & 1) ? K2_T - 1 : 0)), Y = (float)(ty0 + ((cnr & 2) ? TY - 1 : 0));
                 const float cix = affine_coord(T.b0, X, T.b1, Y, T.b2), ciy = affine_coord(T.b3, X, T.b4, Y, T.b5);
                 xmin = fminf(xmin, cix); xmax = fmaxf(xmax, cix); ymin = fminf(ymin, ciy); ymax = fmaxf(ymax, ciy);
             }
@@ -434,7 +439,7 @@ k_gradient_update(const __grid_constant__ CUtensorMap rmap, const float* __restr
                     const f32x2 axp = pk(fmul(T.b0, X0f), fmul(T.b0, X1f)), ayp = pk(fmul(T.b3, X0f), fmul(T.b3, X1f));
 #pragma unroll
                     for (int r = 0; r < K2_ROWS; ++r) {
-                        const float2 rp = rowp[(kc & 1) * K2_T + warp + K2_GW * r];   // row products, built by the fill warps
+                        const float2 rp = rowp[(kc & 1) * TY + warp + K2_GW * r];   // row products, built by the fill warps
                         const float bxr = rp.x, byr = rp.y;
                         const f32x2 ix = add2(add2(axp, pk(bxr, bxr)), b2p);
                         const f32x2 iy = add2(add2(ayp, pk(byr, byr)), b5p);
@@ -461,7 +466,7 @@ k_gradient_update(const __grid_constant__ CUtensorMap rmap, const float* __restr
             // cells wide).  Everything the fill reads was staged by async copies issued two copies earlier by one
             // thread: no address arithmetic, bounds tests or table building is left in these warps.
             const int fw = warp - K2_GW;
-            constexpr int ROWS = (K2_BC + K2_FW - 1) / K2_FW;   // cell rows per fill warp
+            constexpr int ROWS = (K2_UR / 4 + K2_FW - 1) / K2_FW;   // cell rows per fill warp
             const size_t slot0 = (size_t)(b_base + b) * N + k0;
             const int ncw = w + 2 * K2_TPAD, nrw = h + 2 * K2_TPAD;
             auto stage_copy = [&](int kq) {   // one thread: residual box + tap rows of copy kq -> stage (k0+kq) % 4
@@ -505,9 +510,9 @@ k_gradient_update(const __grid_constant__ CUtensorMap rmap, const float* __restr
                         }
                     }
                 }
-                if (live && tid - K2_NG < K2_T) {   // row products of the rotate coordinates for the gather warps
+                if (live && tid - K2_NG < TY) {   // row products of the rotate coordinates for the gather warps
                     const float Yf = (float)(ty0 + tid - K2_NG);
-                    rowp[ub * K2_T + tid - K2_NG] = make_float2(fmul(xfs[kc].b1, Yf), fmul(xfs[kc].b4, Yf));
+                    rowp[ub * TY + tid - K2_NG] = make_float2(fmul(xfs[kc].b1, Yf), fmul(xfs[kc].b4, Yf));
                 }
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&full_bar[ub]);
@@ -909,10 +914,12 @@ static int configure_kernels() {
     if (done) return ASR_OK;
     ASR_CUDA_TRY(cudaFuncSetAttribute(k_forward_residual<K1_XR_SMALL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k1_smem<K1_XR_SMALL>()));
     ASR_CUDA_TRY(cudaFuncSetAttribute(k_forward_residual<K1_XR_BIG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k1_smem<K1_XR_BIG>()));
-    ASR_CUDA_TRY(cudaFuncSetAttribute(k_gradient_update<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K2_SMEM));
-    ASR_CUDA_TRY(cudaFuncSetAttribute(k_gradient_update<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K2_SMEM));
-    ASR_CUDA_TRY(cudaFuncSetAttribute(k_gradient_update<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K2_SMEM));
-    ASR_CUDA_TRY(cudaFuncSetAttribute(k_gradient_update<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K2_SMEM));
+#define ASR_K2_ATTR(WG, BT, TY) \
+    ASR_CUDA_TRY(cudaFuncSetAttribute(k_gradient_update<WG, BT, TY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k2_smem<TY>()));
+#define ASR_K2_ATTRS(TY) ASR_K2_ATTR(false, false, TY) ASR_K2_ATTR(false, true, TY) ASR_K2_ATTR(true, false, TY) ASR_K2_ATTR(true, true, TY)
+    ASR_K2_ATTRS(64) ASR_K2_ATTRS(32)
+#undef ASR_K2_ATTRS
+#undef ASR_K2_ATTR
     done = true;
     return ASR_OK;
 }
@@ -935,6 +942,30 @@ extern "C" int asr_solve_workspace_bytes(int B, int N, int h, int w, int H, int 
     *bytes = make_layout(B, N, h, w, H, W, max_iter).total;
     return ASR_OK;
 }
+
+// K2 tile height: 64 rows unless that leaves SMs without a CTA (a 512^2 image is only 64 tiles of 64x64), then 32: measured on
+// B200 the 32-row tiles win for one image (K2 104 -> 79 us per iteration), tie for two, lose from four on (halo of the u tile).
+// 16-row tiles were measured too and never win.  ASR_K2_TY overrides the choice (experiments, tests of both variants).
+static int k2_tile_height(int n_images, int H, int W) {
+    if (const char* e = getenv("ASR_K2_TY")) { const int v = atoi(e); if (v == 64 || v == 32) return v; }
+    int n_sm = 148;
+    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, 0);
+    const long long tiles64 = (long long)((W + K2_T - 1) / K2_T) * ((H + 63) / 64);
+    return (long long)n_images * tiles64 < n_sm ? 32 : 64;
+}
+#define ASR_LAUNCH_K2_TY(WG, BT, TY, ntiles, nimg, st, ...) \
+    ASR_LAUNCH_TIMED(1, (k_gradient_update<WG, BT, TY>), dim3(ntiles, nimg), K2_THREADS, (k2_smem<TY>()), st, __VA_ARGS__)
+#define ASR_LAUNCH_K2(WG, btv, ty, H, W, nimg, st, ...)                                                               \
+    do {                                                                                                              \
+        const int ntiles_ = ((W + K2_T - 1) / K2_T) * ((H + (ty) - 1) / (ty));                                        \
+        if (btv) {                                                                                                    \
+            if ((ty) == 64) ASR_LAUNCH_K2_TY(WG, true, 64, ntiles_, nimg, st, __VA_ARGS__);                           \
+            else ASR_LAUNCH_K2_TY(WG, true, 32, ntiles_, nimg, st, __VA_ARGS__);                                      \
+        } else {                                                                                                      \
+            if ((ty) == 64) ASR_LAUNCH_K2_TY(WG, false, 64, ntiles_, nimg, st, __VA_ARGS__);                          \
+            else ASR_LAUNCH_K2_TY(WG, false, 32, ntiles_, nimg, st, __VA_ARGS__);                                     \
+        }                                                                                                             \
+    } while (0)
 
 static int solve_impl(const AsrSolveParams* params, int n_params, const float* d_copies, const float* h_angles,
                       const float* h_shifts, const uint8_t* h_keep, const int32_t* h_stack_index, int B, int N, int h, int w,
@@ -962,7 +993,6 @@ static int solve_impl(const AsrSolveParams* params, int n_params, const float* d
 
     const int ntj = (w + K1_TJ - 1) / K1_TJ;
     const int t1 = ntj * ((h + K1_TI - 1) / K1_TI);
-    const int t2 = ((W + K2_T - 1) / K2_T) * ((H + K2_T - 1) / K2_T);
     CUtensorMap map_a, map_b, map_r;
     const int box_rows = T.small_box ? K1_XR_SMALL : K1_XR_BIG;
     const int wp = pitch4(w);
@@ -976,6 +1006,7 @@ static int solve_impl(const AsrSolveParams* params, int n_params, const float* d
         int iters = 0;
         for (int b = b0; b < b0 + nb; ++b) iters = T.hp[b].num_iter > iters ? T.hp[b].num_iter : iters;
         const size_t po = (size_t)b0 * plane, ro = (size_t)b0 * N * h * wp;
+        const int ty = k2_tile_height(nb, H, W);
         for (int it = 0; it < iters; ++it) {
             float* xc = ((it & 1) ? D.xb : D.xa) + po;
             float* xn = ((it & 1) ? D.xa : D.xb) + po;
@@ -987,14 +1018,8 @@ static int solve_impl(const AsrSolveParams* params, int n_params, const float* d
                 ASR_LAUNCH_TIMED(0, k_forward_residual<K1_XR_BIG>, dim3(t1, T.max_kept, nb), K1_THREADS, k1_smem<K1_XR_BIG>(), st,
                     (it & 1) ? map_b : map_a, d_copies, D.resid + ro, D.fwd + (size_t)b0 * N, D.src + (size_t)b0 * N, D.ip + b0,
                     it, N, h, w, wp, H, W, ntj, div_magic(ntj), b0);
-            if (T.any_btv)
-                ASR_LAUNCH_TIMED(1, (k_gradient_update<false, true>), dim3(t2, nb), K2_THREADS, K2_SMEM, st, map_r,
-                    xc, xn, D.s0 + po, D.s1 + po, D.s2 + po, D.tapc, D.tapr, D.inv + (size_t)b0 * N, D.ip + b0,
-                    D.sched + b0, it, N, h, w, H, W, B, b0);
-            else
-                ASR_LAUNCH_TIMED(1, (k_gradient_update<false, false>), dim3(t2, nb), K2_THREADS, K2_SMEM, st, map_r,
-                    xc, xn, D.s0 + po, D.s1 + po, D.s2 + po, D.tapc, D.tapr, D.inv + (size_t)b0 * N, D.ip + b0,
-                    D.sched + b0, it, N, h, w, H, W, B, b0);
+            ASR_LAUNCH_K2(false, T.any_btv, ty, H, W, nb, st, map_r, xc, xn, D.s0 + po, D.s1 + po, D.s2 + po, D.tapc, D.tapr,
+                          D.inv + (size_t)b0 * N, D.ip + b0, D.sched + b0, it, N, h, w, H, W, B, b0);
         }
     }
     ASR_CUDA_TRY(cudaGetLastError());
@@ -1048,7 +1073,6 @@ extern "C" int asr_loss_grad_batched(const AsrSolveParams* params, int n_params,
     ASR_CUDA_TRY(cudaMemcpyAsync(D.xa, d_x, sizeof(float) * B * plane, cudaMemcpyDeviceToDevice, st));
     const int ntj = (w + K1_TJ - 1) / K1_TJ;
     const int t1 = ntj * ((h + K1_TI - 1) / K1_TI);
-    const int t2 = ((W + K2_T - 1) / K2_T) * ((H + K2_T - 1) / K2_T);
     CUtensorMap map_a, map_r;
     const int wp = pitch4(w);
     if (int e = make_x_map(&map_a, D.xa, B, H, W, T.small_box ? K1_XR_SMALL : K1_XR_BIG)) return e;
@@ -1060,12 +1084,8 @@ extern "C" int asr_loss_grad_batched(const AsrSolveParams* params, int n_params,
     else
         ASR_LAUNCH_TIMED(0, k_forward_residual<K1_XR_BIG>, dim3(t1, T.max_kept, B), K1_THREADS, k1_smem<K1_XR_BIG>(), st, map_a, d_copies,
                          D.resid, D.fwd, D.src, D.ip, 0, N, h, w, wp, H, W, ntj, div_magic(ntj), 0);
-    if (T.any_btv)
-        ASR_LAUNCH_TIMED(1, (k_gradient_update<true, true>), dim3(t2, B), K2_THREADS, K2_SMEM, st, map_r, D.xa, D.xb, D.s0, D.s1, D.s2,
-                         D.tapc, D.tapr, D.inv, D.ip, D.sched, 0, N, h, w, H, W, B, 0);
-    else
-        ASR_LAUNCH_TIMED(1, (k_gradient_update<true, false>), dim3(t2, B), K2_THREADS, K2_SMEM, st, map_r, D.xa, D.xb, D.s0, D.s1, D.s2,
-                         D.tapc, D.tapr, D.inv, D.ip, D.sched, 0, N, h, w, H, W, B, 0);
+    ASR_LAUNCH_K2(true, T.any_btv, k2_tile_height(B, H, W), H, W, B, st, map_r, D.xa, D.xb, D.s0, D.s1, D.s2, D.tapc, D.tapr, D.inv, D.ip,
+                  D.sched, 0, N, h, w, H, W, B, 0);
     ASR_CUDA_TRY(cudaGetLastError());
     if (d_grad) ASR_CUDA_TRY(cudaMemcpyAsync(d_grad, D.xb, sizeof(float) * B * plane, cudaMemcpyDeviceToDevice, st));
     if (d_resid) {

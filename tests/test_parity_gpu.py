@@ -82,6 +82,17 @@ def test_solve_bit_identical_to_oracle(case):
         assert_loss_close(float(loss[b]), lo)
 
 
+@pytest.mark.parametrize("ty", ["32", "64"])
+def test_both_gradient_tile_heights(ty, monkeypatch):
+    """K2 runs 64x32 tiles for one or two images and 64x64 tiles otherwise; ASR_K2_TY forces either on the same input"""
+    monkeypatch.setenv("ASR_K2_TY", ty)
+    copies, ang, sh = synth(3, 9, (32, 48), 0.7, 30, seed=55)
+    x = A.solve_batched(copies, ang, sh, A.SolveParams(num_iter=7))
+    for b in range(3):
+        xo, _ = O.augmented_superresolution(copies[b].cpu().numpy(), ang[b], sh[b], O.SolveParams(num_iter=7), output_size=(128, 192))
+        np.testing.assert_array_equal(x[b].cpu().numpy(), xo[..., 0])
+
+
 def test_single_evaluation_residual_and_gradient():
     copies, ang, sh = synth(2, 9, (32, 32), 0.6, 40, seed=21)
     g = torch.Generator(device="cuda").manual_seed(0)
