@@ -278,9 +278,10 @@ k_forward_residual(const __grid_constant__ CUtensorMap xmap, const float* __rest
 constexpr int K2_T = 64;               // HR tile width; the tile height TY is 64 for batches that fill the GPU and 32 for one or two images
                                        // (one 512^2 image is only 64 tiles of 64x64: such a solve is latency-bound, 104 -> 79 us per iteration)
 constexpr int K2_GW = 8;               // gather warps; thread owns pixels (lane + 32c, warp + 8r), c<2, r<TY/8
-constexpr int K2_FW = 4;               // fill warps
-constexpr int K2_NG = 32 * K2_GW, K2_NF = 32 * K2_FW;
-constexpr int K2_THREADS = K2_NG + K2_NF;
+// fill warps: 4 in the throughput variant (64-row tiles, two CTAs per SM); 8 in the latency variant (32-row tiles, one lone CTA per
+// SM, where the fill warps' serial latency per copy is what the gather warps wait for)
+template <int TY> struct K2Fill { static constexpr int warps = TY == 64 ? 4 : 8, threads = 32 * (K2_GW + warps), ctas = TY == 64 ? 2 : 1; };
+constexpr int K2_NG = 32 * K2_GW;
 constexpr int K2_US = 96;              // u tile stride: 64*sqrt(2)+2+3 < 96, multiple of 32
 template <int TY> struct K2Rows { static constexpr int value = TY == 64 ? 96 : 80; };   // u tile rows: sqrt(63^2+(TY-1)^2)+2 -> cells
 constexpr int K2_CHUNK = 128;          // copies whose boxes/transforms are staged at once
@@ -345,7 +346,7 @@ __global__ void k_tap_tables(const InvXf* __restrict__ inv, float2* __restrict__
 }
 
 template <bool WRITE_GRAD, bool BTV, int TY>
-__global__ void __launch_bounds__(K2_THREADS, 2)
+__global__ void __launch_bounds__(K2Fill<TY>::threads, K2Fill<TY>::ctas)
 k_gradient_update(const __grid_constant__ CUtensorMap rmap, const float* __restrict__ x_cur, float* __restrict__ x_next,
                   float* __restrict__ s0, float* __restrict__ s1, float* __restrict__ s2, const float2* __restrict__ tapc,
                   const float2* __restrict__ tapr, const InvXf* __restrict__ inv, const ImgParams* __restrict__ ip,
@@ -354,7 +355,7 @@ k_gradient_update(const __grid_constant__ CUtensorMap rmap, const float* __restr
     const ImgParams P = ip[b];
     if (it >= P.num_iter) return;
 
-    constexpr int K2_UR = K2Rows<TY>::value, K2_ROWS = TY / K2_GW;
+    constexpr int K2_UR = K2Rows<TY>::value, K2_ROWS = TY / K2_GW, K2_FW = K2Fill<TY>::warps, K2_THREADS = K2Fill<TY>::threads;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float* ut = reinterpret_cast<float*>(smem_raw);                       // [2][K2_UR][K2_US]
     K2Stage* stages = reinterpret_cast<K2Stage*>(ut + 2 * K2_US * K2_UR);  // [K2_STAGES]
@@ -943,18 +944,18 @@ extern "C" int asr_solve_workspace_bytes(int B, int N, int h, int w, int H, int 
     return ASR_OK;
 }
 
-// K2 tile height: 64 rows unless that leaves SMs without a CTA (a 512^2 image is only 64 tiles of 64x64), then 32: measured on
-// B200 the 32-row tiles win for one image (K2 104 -> 79 us per iteration), tie for two, lose from four on (halo of the u tile).
-// 16-row tiles were measured too and never win.  ASR_K2_TY overrides the choice (experiments, tests of both variants).
+// K2 tile height: 64 rows unless the whole solve fits one 64x32 CTA per SM (a 512^2 image is only 64 tiles of 64x64: a single
+// image leaves most SMs idle and every CTA latency-bound; measured K2 104 -> 73 us per iteration with 32-row tiles and 8 fill
+// warps).  16-row tiles and four u buffers were measured too and never win.  ASR_K2_TY overrides the choice (tests, experiments).
 static int k2_tile_height(int n_images, int H, int W) {
     if (const char* e = getenv("ASR_K2_TY")) { const int v = atoi(e); if (v == 64 || v == 32) return v; }
     int n_sm = 148;
     cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, 0);
-    const long long tiles64 = (long long)((W + K2_T - 1) / K2_T) * ((H + 63) / 64);
-    return (long long)n_images * tiles64 < n_sm ? 32 : 64;
+    const long long tiles32 = (long long)((W + K2_T - 1) / K2_T) * ((H + 31) / 32);
+    return (long long)n_images * tiles32 <= n_sm ? 32 : 64;   // the 32-row variant runs one CTA per SM
 }
 #define ASR_LAUNCH_K2_TY(WG, BT, TY, ntiles, nimg, st, ...) \
-    ASR_LAUNCH_TIMED(1, (k_gradient_update<WG, BT, TY>), dim3(ntiles, nimg), K2_THREADS, (k2_smem<TY>()), st, __VA_ARGS__)
+    ASR_LAUNCH_TIMED(1, (k_gradient_update<WG, BT, TY>), dim3(ntiles, nimg), K2Fill<TY>::threads, (k2_smem<TY>()), st, __VA_ARGS__)
 #define ASR_LAUNCH_K2(WG, btv, ty, H, W, nimg, st, ...)                                                               \
     do {                                                                                                              \
         const int ntiles_ = ((W + K2_T - 1) / K2_T) * ((H + (ty) - 1) / (ty));                                        \
