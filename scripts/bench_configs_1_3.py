@@ -2,7 +2,7 @@
    config 1: test_SR.py path: 1 synthetic image, 100 copies {0,8}, 128^2 -> 512^2, 300 Adam+AMSGrad iterations, threshold 0.2, class 8
    config 3: max-OPM pipeline on random logits: warp 100 RGB copies, slice_max OPM extraction, two solves (class and max maps),
              threshold class >= max
-Prints one JSON object; the CPU oracle is timed next to config 1 on a bounded sample (--oracle-iters)."""
+Prints one JSON object."""
 import json, os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
@@ -11,7 +11,6 @@ from deeplabv3plus_augmented_superresolution_b200.superresolution_scripts.optimi
 from deeplabv3plus_augmented_superresolution_b200.superresolution_scripts.superresolution import Superresolution
 from deeplabv3plus_augmented_superresolution_b200.superresolution_scripts import augmentation_utils as AU, superres_utils as SU
 
-oracle_iters = int(sys.argv[1]) if len(sys.argv) > 1 else 30
 
 
 def solver():
@@ -36,13 +35,12 @@ def config1():
     x, _ = solver().augmented_superresolution(clist, ang[0], sh[0])
     return SU.threshold_image(x, 8, th_factor=0.2)
 s1 = wall(config1)
-from oracle import oracle as O
-O.use_all_cores()
-t = time.perf_counter()
-O.augmented_superresolution(copies[0].numpy(), ang[0], sh[0], O.SolveParams(num_iter=oracle_iters), output_size=(512, 512))
-so = (time.perf_counter() - t) / oracle_iters * 300
-out["config1_test_SR"] = {"gpu_seconds_per_image": s1, "gpu_images_per_s": 1 / s1, "cpu_oracle_seconds_per_image": so,
-                          "cpu_cores": O.num_threads(), "cpu_sample": f"{oracle_iters} of 300 iterations, extrapolated", "speedup": so / s1}
+# the CPU side of this config is bench.py's cpu_baseline (the oracle is test infrastructure: only tests/, smoke() and
+# bench.py's cpu_baseline / --impl reference legs execute it); pass its images/s as argv[1] to get the ratio
+cpu_ips = float(sys.argv[1]) if len(sys.argv) > 1 else None
+out["config1_test_SR"] = {"gpu_seconds_per_image": s1, "gpu_images_per_s": 1 / s1}
+if cpu_ips:
+    out["config1_test_SR"].update({"cpu_oracle_images_per_s_from_bench_py": cpu_ips, "speedup": (1 / s1) / cpu_ips})
 # ---- config 3 ----------------------------------------------------------------------------------------------
 g = torch.Generator(device="cuda").manual_seed(0)
 img = torch.rand((512, 512, 3), device="cuda", generator=g).cpu().numpy()
