@@ -183,7 +183,7 @@ __global__ void k_copy_minmax(const float* __restrict__ logits, size_t per_copy,
     const int n = blockIdx.y;
     const float* p = logits + (size_t)n * per_copy;
     float lo = INFINITY, hi = -INFINITY;
-    const size_t n4 = per_copy / 4;
+    const size_t n4 = ((reinterpret_cast<uintptr_t>(p) & 15) == 0) ? per_copy / 4 : 0;   // odd per-copy sizes misalign every other copy: scalar path
     const float4* p4 = reinterpret_cast<const float4*>(p);
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
         const float4 v = __ldg(p4 + i);
@@ -594,6 +594,7 @@ extern "C" int asr_warp_affine(const float* d_image, const float* h_angles, cons
     if (N > 65535) return fail(ASR_EINVAL, "N must be <= 65535");
     if (H > (1 << 20) || W > (1 << 20)) return fail(ASR_EINVAL, "image too large for the fp32 floor trick");
     if (interp != ASR_INTERP_NEAREST && interp != ASR_INTERP_BILINEAR) return fail(ASR_EINVAL, "unknown interpolation %d", interp);
+    if (!aligned16(d_image) || !aligned16(d_out)) return fail(ASR_EINVAL, "device pointers must be 16-byte aligned");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     std::vector<WarpXf> xf(N);
     for (int k = 0; k < N; ++k) {
@@ -603,9 +604,10 @@ extern "C" int asr_warp_affine(const float* d_image, const float* h_angles, cons
     }
     // transient, stream-ordered scratch: the per-copy table and the image padded to 4 channels
     const size_t npx = (size_t)H * W;
-    unsigned char* scratch = nullptr;
+    AsyncScratch guard;   // released in stream order on every return path
     const size_t xf_bytes = (sizeof(WarpXf) * N + 255) / 256 * 256;
-    ASR_CUDA_TRY(cudaMallocAsync((void**)&scratch, xf_bytes + sizeof(float4) * npx, st));
+    ASR_CUDA_TRY(guard.alloc(xf_bytes + sizeof(float4) * npx, st));
+    unsigned char* scratch = static_cast<unsigned char*>(guard.p);
     WarpXf* d_xf = reinterpret_cast<WarpXf*>(scratch);
     float4* d_pad = reinterpret_cast<float4*>(scratch + xf_bytes);
     ASR_CUDA_TRY(cudaMemcpyAsync(d_xf, xf.data(), sizeof(WarpXf) * N, cudaMemcpyHostToDevice, st));
@@ -618,7 +620,6 @@ extern "C" int asr_warp_affine(const float* d_image, const float* h_angles, cons
     default: ASR_LAUNCH(k_warp_affine<4>, dim3(tiles, N), K3_THREADS, 0, st, d_pad, d_xf, d_out, H, W, interp); break;
     }
     ASR_CUDA_TRY(cudaGetLastError());
-    ASR_CUDA_TRY(cudaFreeAsync(scratch, st));
     return ASR_OK;
 }
 
@@ -631,6 +632,8 @@ extern "C" int asr_opm_extract(const float* d_logits, int N, int h, int w, int K
     if (mode == ASR_OPM_SLICE_MAX && !d_max_out) return fail(ASR_ENULL, "slice_max needs d_max_out");
     if (mode == ASR_OPM_SLICE && !d_workspace) return fail(ASR_ENULL, "slice needs a 2*N float workspace");
     if (N > 65535) return fail(ASR_EINVAL, "N must be <= 65535");
+    if (!aligned16(d_logits) || !aligned16(d_class_out) || !aligned16(d_max_out) || !aligned16(d_workspace))
+        return fail(ASR_EINVAL, "device pointers must be 16-byte aligned");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const size_t px = (size_t)h * w;
     unsigned* mm = static_cast<unsigned*>(d_workspace);
@@ -638,11 +641,9 @@ extern "C" int asr_opm_extract(const float* d_logits, int N, int h, int w, int K
         ASR_LAUNCH(k_mm_init, (N + 127) / 128, 128, 0, st, mm, N);
         ASR_LAUNCH(k_copy_minmax, dim3(32, N), 256, 0, st, d_logits, px * K, mm);
     }
-    static bool attr = false;
-    if (!attr) {
+    static unsigned long long attr = 0;
+    if (first_use_on_device(&attr))
         ASR_CUDA_TRY(cudaFuncSetAttribute(k_opm_extract, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(float) * K4_THREADS * K4_KMAX)));
-        attr = true;
-    }
     const unsigned blocks = (unsigned)((px + K4_THREADS - 1) / K4_THREADS);
     ASR_LAUNCH(k_opm_extract, dim3(blocks, N), K4_THREADS, sizeof(float) * K4_THREADS * K, st, d_logits, K, px, class_id, mode, mm,
                                                                                       d_class_out, d_max_out);
@@ -684,6 +685,7 @@ extern "C" int asr_backproject_batched(int mode, const float* d_copies, const fl
     if (!d_copies || !h_angles || !h_shifts || !d_out) return fail(ASR_ENULL, "null argument");
     if (mode != ASR_BACKPROJECT_MAX && mode != ASR_BACKPROJECT_MEAN) return fail(ASR_EINVAL, "mode must be max or mean");
     if (B <= 0 || N <= 0 || h <= 0 || w <= 0 || H <= 0 || W <= 0 || B > 65535) return fail(ASR_EINVAL, "bad shape");
+    if (!aligned16(d_copies) || !aligned16(d_out)) return fail(ASR_EINVAL, "device pointers must be 16-byte aligned");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     std::vector<BackXf> xf((size_t)B * N);
     for (size_t i = 0; i < xf.size(); ++i) {
@@ -692,21 +694,19 @@ extern "C" int asr_backproject_batched(int mode, const float* d_copies, const fl
         // tfa.image.translate(..., -shifts): transform offsets -(-dx), -(-dy)
         xf[i] = BackXf{r[0], r[1], r[2], r[3], r[4], r[5], -(-h_shifts[2 * i]), -(-h_shifts[2 * i + 1])};
     }
-    BackXf* d_xf = nullptr;
-    ASR_CUDA_TRY(cudaMallocAsync((void**)&d_xf, sizeof(BackXf) * xf.size(), st));
+    AsyncScratch scratch;   // released in stream order on every return path
+    ASR_CUDA_TRY(scratch.alloc(sizeof(BackXf) * xf.size(), st));
+    BackXf* d_xf = static_cast<BackXf*>(scratch.p);
     ASR_CUDA_TRY(cudaMemcpyAsync(d_xf, xf.data(), sizeof(BackXf) * xf.size(), cudaMemcpyHostToDevice, st));
     if (H == 4 * h && W == 4 * w) {
-        static bool attr = false;
-        if (!attr) {
+        static unsigned long long attr = 0;
+        if (first_use_on_device(&attr))
             ASR_CUDA_TRY(cudaFuncSetAttribute(k_backproject_tiled, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K5_SMEM));
-            attr = true;
-        }
         const int tiles = ((W + K5_T - 1) / K5_T) * ((H + K5_T - 1) / K5_T);
         ASR_LAUNCH(k_backproject_tiled, dim3(tiles, B), K5_THREADS, K5_SMEM, st, d_copies, d_xf, d_out, mode, N, h, w, H, W);
     } else {
         ASR_LAUNCH(k_backproject, dim3((W + 31) / 32, (H + 7) / 8, B), 256, 0, st, d_copies, d_xf, d_out, mode, N, h, w, H, W);
     }
     ASR_CUDA_TRY(cudaGetLastError());
-    ASR_CUDA_TRY(cudaFreeAsync(d_xf, st));
     return ASR_OK;
 }

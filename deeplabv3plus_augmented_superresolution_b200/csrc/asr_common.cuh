@@ -26,6 +26,20 @@ int fail(int code, const char* fmt, ...);
         if (_e != cudaSuccess) return ::asr::fail(ASR_ECUDA, "%s: %s", #expr, cudaGetErrorString(_e)); \
     } while (0)
 
+// Attributes set with cudaFuncSetAttribute belong to the (function, device) pair, so "done once" is tracked per
+// device: returns true the first time it is called with `mask` on the current device (bit = device ordinal;
+// ordinals >= 64 simply repeat the cheap call every time).  A benign race at worst repeats the call.
+bool first_use_on_device(unsigned long long* mask);
+// device pointers handed to the library must be 16-byte aligned (float4 / TMA / 128-bit stores); see include/asr.h
+static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+// stream-ordered scratch that is released on every return path
+struct AsyncScratch {
+    void* p = nullptr;
+    cudaStream_t st = nullptr;
+    cudaError_t alloc(size_t bytes, cudaStream_t s) { st = s; return cudaMallocAsync(&p, bytes, s); }
+    ~AsyncScratch() { if (p) cudaFreeAsync(p, st); }
+};
+
 // ---- launch accounting / optional per-kernel timing (asr_kernel_launches, asr_profile_*) -------
 // Every kernel launch of the library goes through ASR_LAUNCH so that bench.py can report how many of
 // our kernels ran in its timed region; with profiling on, the two solve kernels are bracketed by
@@ -92,15 +106,23 @@ __device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) { f32x2 r; asm("add.rn.f
 __device__ __forceinline__ f32x2 sub2(f32x2 a, f32x2 b) { f32x2 r; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
 __device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) { f32x2 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
 __device__ __forceinline__ f32x2 add2_rd(f32x2 a, f32x2 b) { f32x2 r; asm("add.rm.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
-// bilerp() on two pixels at once.  ptxas (12.9) contracts a packed multiply feeding a packed add into FFMA2
-// even when both carry an explicit .rn (it never does so for scalar ops, nor across a scalar/packed
-// boundary), so the products are packed and the sums scalar: same FMA-pipe time, three more issue slots.
+// fma.rn.f32x2 is used for two things only, neither of which fuses a product of the op sequence into a sum:
+// (a) an exact packed ADD written as m*1.0 + n (see sum2), (b) shared-memory address arithmetic on small integers.
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) { f32x2 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
+// (1.0f, 1.0f) in constant memory: a value ptxas cannot see, so the fma below is not simplified back into an add
+static __constant__ f32x2 c_one2 = 0x3f8000003f800000ull;
+// a + b on both lanes where a and/or b are packed PRODUCTS.  ptxas (12.9) contracts a packed multiply feeding a packed
+// add into one FFMA2 even when both carry an explicit .rn (it never does so for scalar ops), which would round the
+// product and the sum once instead of twice.  An FFMA2 cannot absorb a second multiply, so the sum is issued as
+// fma(a, 1.0, b): a*1.0 is exact and the single rounding of a*1.0 + b is the rounding of the IEEE add a + b
+// (signed zeros included), i.e. the result is bit-identical to add.rn.  One issue slot per pixel pair instead of two
+// scalar FADDs, same FMA-pipe time.
+__device__ __forceinline__ f32x2 sum2(f32x2 a, f32x2 b) { return fma2(a, c_one2, b); }
+// bilerp() on two pixels at once: 6 FMUL2 + 3 exact packed sums
 __device__ __forceinline__ f32x2 bilerp2(f32x2 v00, f32x2 v01, f32x2 v10, f32x2 v11, f32x2 wx0, f32x2 wx1, f32x2 wy0, f32x2 wy1) {
-    const f32x2 m00 = mul2(wx0, v00), m01 = mul2(wx1, v01), m10 = mul2(wx0, v10), m11 = mul2(wx1, v11);
-    const f32x2 top = pk(fadd(pk_lo(m00), pk_lo(m01)), fadd(pk_hi(m00), pk_hi(m01)));
-    const f32x2 bot = pk(fadd(pk_lo(m10), pk_lo(m11)), fadd(pk_hi(m10), pk_hi(m11)));
-    const f32x2 n0 = mul2(wy0, top), n1 = mul2(wy1, bot);
-    return pk(fadd(pk_lo(n0), pk_lo(n1)), fadd(pk_hi(n0), pk_hi(n1)));
+    const f32x2 top = sum2(mul2(wx0, v00), mul2(wx1, v01));
+    const f32x2 bot = sum2(mul2(wx0, v10), mul2(wx1, v11));
+    return sum2(mul2(wy0, top), mul2(wy1, bot));
 }
 
 // shared-memory address of tap (y0,x0): 4*(raw_y*STRIDE + raw_x) + cst4, where cst4 folds the magic bias of the

@@ -77,7 +77,8 @@ static bool g_prof_on = false;
 struct ProfSpan { cudaEvent_t a, b; int slot; };
 static std::vector<ProfSpan> g_spans;
 static std::vector<cudaEvent_t> g_pool;
-static cudaEvent_t g_open[2];
+struct OpenMark { int slot; cudaStream_t st; cudaEvent_t ev; };
+static std::vector<OpenMark> g_open;   // begin marks waiting for their end mark, keyed by (slot, stream)
 
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
@@ -92,13 +93,26 @@ void profile_mark(int slot, cudaStream_t st, bool begin) {
     if (!g_prof_on) return;
     std::lock_guard<std::mutex> lk(g_prof_mu);
     if (begin) {
-        g_open[slot] = take_event();
-        cudaEventRecord(g_open[slot], st);
-    } else {
         cudaEvent_t e = take_event();
         cudaEventRecord(e, st);
-        g_spans.push_back(ProfSpan{g_open[slot], e, slot});
+        g_open.push_back(OpenMark{slot, st, e});
+    } else {
+        for (size_t i = g_open.size(); i-- > 0;) {
+            if (g_open[i].slot != slot || g_open[i].st != st) continue;
+            cudaEvent_t e = take_event();
+            cudaEventRecord(e, st);
+            g_spans.push_back(ProfSpan{g_open[i].ev, e, slot});
+            g_open.erase(g_open.begin() + (long)i);
+            return;
+        }
     }
+}
+
+bool first_use_on_device(unsigned long long* mask) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return true;
+    const unsigned long long bit = 1ull << dev;
+    return (__atomic_fetch_or(mask, bit, __ATOMIC_RELAXED) & bit) == 0;
 }
 
 }  // namespace asr

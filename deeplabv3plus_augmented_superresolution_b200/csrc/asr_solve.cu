@@ -911,8 +911,8 @@ static int make_r_map(CUtensorMap* map, const float* base, int BN, int h, int w)
 static unsigned div_magic(int d) { return (unsigned)((0x100000000ull + (unsigned)d - 1) / (unsigned)d); }   // __umulhi(n, magic) == n / d for n*d < 2^32
 
 static int configure_kernels() {
-    static bool done = false;   // attribute is per-function, idempotent; a benign race at worst repeats it
-    if (done) return ASR_OK;
+    static unsigned long long done = 0;   // one bit per device: the attribute belongs to the (function, device) pair
+    if (!first_use_on_device(&done)) return ASR_OK;
     ASR_CUDA_TRY(cudaFuncSetAttribute(k_forward_residual<K1_XR_SMALL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k1_smem<K1_XR_SMALL>()));
     ASR_CUDA_TRY(cudaFuncSetAttribute(k_forward_residual<K1_XR_BIG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k1_smem<K1_XR_BIG>()));
 #define ASR_K2_ATTR(WG, BT, TY) \
@@ -921,7 +921,6 @@ static int configure_kernels() {
     ASR_K2_ATTRS(64) ASR_K2_ATTRS(32)
 #undef ASR_K2_ATTRS
 #undef ASR_K2_ATTR
-    done = true;
     return ASR_OK;
 }
 
@@ -949,8 +948,8 @@ extern "C" int asr_solve_workspace_bytes(int B, int N, int h, int w, int H, int 
 // warps).  16-row tiles and four u buffers were measured too and never win.  ASR_K2_TY overrides the choice (tests, experiments).
 static int k2_tile_height(int n_images, int H, int W) {
     if (const char* e = getenv("ASR_K2_TY")) { const int v = atoi(e); if (v == 64 || v == 32) return v; }
-    int n_sm = 148;
-    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, 0);
+    int n_sm = 148, dev = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
     const long long tiles32 = (long long)((W + K2_T - 1) / K2_T) * ((H + 31) / 32);
     return (long long)n_images * tiles32 <= n_sm ? 32 : 64;   // the 32-row variant runs one CTA per SM
 }
@@ -975,6 +974,8 @@ static int solve_impl(const AsrSolveParams* params, int n_params, const float* d
     if (n_params != 1 && n_params != B) return fail(ASR_EINVAL, "n_params must be 1 or B");
     if (int e = check_shapes(B, N, h, w, H, W)) return e;
     if (int e = check_params(params, n_params)) return e;
+    if (!aligned16(d_copies) || !aligned16(d_x_out) || (reinterpret_cast<uintptr_t>(d_workspace) & 255u))
+        return fail(ASR_EINVAL, "d_copies / d_x_out must be 16-byte aligned and d_workspace 256-byte aligned");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
 
     HostTables T;
@@ -1058,6 +1059,8 @@ extern "C" int asr_loss_grad_batched(const AsrSolveParams* params, int n_params,
     if (n_params != 1 && n_params != B) return fail(ASR_EINVAL, "n_params must be 1 or B");
     if (int e = check_shapes(B, N, h, w, H, W)) return e;
     if (int e = check_params(params, n_params)) return e;
+    if (!aligned16(d_copies) || !aligned16(d_x) || (reinterpret_cast<uintptr_t>(d_workspace) & 255u))
+        return fail(ASR_EINVAL, "d_copies / d_x must be 16-byte aligned and d_workspace 256-byte aligned");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
 
     std::vector<AsrSolveParams> one(params, params + n_params);

@@ -19,6 +19,11 @@
  *     only allocations are transient per-copy transform tables (32 bytes per copy) made and freed
  *     in stream order inside asr_warp_affine / asr_backproject_batched.
  *   - all images are fp32, C-contiguous.  There is no CPU fallback.
+ *   - alignment: every device array must be 16-byte aligned and every `d_workspace` 256-byte aligned
+ *     (128-bit loads/stores and TMA tensor maps); any cudaMalloc / torch allocation satisfies both.
+ *     A misaligned pointer is rejected with ASR_EINVAL, never dereferenced.
+ *   - thread-safety: re-entrant; one host thread per GPU may call concurrently, and one process may
+ *     drive several GPUs in turn (per-device kernel attributes are tracked per device).
  */
 #ifndef ASR_H
 #define ASR_H

@@ -420,3 +420,44 @@ def test_dlpack_entry_point():
     rc = L.asr_solve_batched_dlpack(arr, n, C.pythonapi.PyCapsule_GetPointer(cpu_cap, b"dltensor"), a.ctypes.data_as(_lib._fp),
                                     s.ctypes.data_as(_lib._fp), None, ptrs[1], None, ptrs[2], None)
     assert rc == -6
+
+
+# --------------------------------------------------------------------------------------------------
+# one process, several GPUs: kernel attributes (dynamic shared memory limits) and the SM count are per device
+# --------------------------------------------------------------------------------------------------
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two CUDA devices")
+def test_same_process_second_device():
+    from deeplabv3plus_augmented_superresolution_b200.synthetic import make_augmented_copies
+    from deeplabv3plus_augmented_superresolution_b200.superresolution_scripts.superresolution import Superresolution
+    P = A.SolveParams(num_iter=6)
+    sr = Superresolution(feature_size=(32, 32), output_size=(128, 128))
+    outs = []
+    for dev in ("cuda:0", "cuda:1", "cuda:0"):
+        copies, ang, sh = make_augmented_copies(1, 5, (32, 32), (128, 128), 0.15, 20, seed=21, device=dev)
+        x = A.solve_batched(copies, ang, sh, P)
+        mx = sr.backproject_batched(copies, ang, sh, "max")
+        torch.cuda.synchronize(dev)
+        outs.append((x.cpu().numpy(), mx.cpu().numpy()))
+    xo, _ = O.augmented_superresolution(copies[0].cpu().numpy(), ang[0], sh[0], O.SolveParams(num_iter=6), output_size=(128, 128))
+    for x, mx in outs:
+        assert np.array_equal(x[0], xo[..., 0])
+        assert np.array_equal(mx, outs[0][1])
+
+
+def test_misaligned_pointers_are_rejected():
+    copies, ang, sh = synth(1, 3, (16, 16))
+    L = A.lib()
+    need = C.c_size_t()
+    A.check(L.asr_solve_workspace_bytes(1, 3, 16, 16, 64, 64, 2, C.byref(need)))
+    ws = torch.empty(need.value + 512, dtype=torch.uint8, device="cuda")
+    x = torch.empty((1, 64, 64), dtype=torch.float32, device="cuda")
+    arr, n = A._params_array(A.SolveParams(num_iter=2))
+    a32, s32 = np.ascontiguousarray(ang, np.float32), np.ascontiguousarray(sh, np.float32)
+    fp = C.POINTER(C.c_float)
+    rc = L.asr_solve_batched(arr, n, copies.data_ptr() + 4, a32.ctypes.data_as(fp), s32.ctypes.data_as(fp), None, 1, 3, 16, 16, 64, 64,
+                             x.data_ptr(), None, ws.data_ptr(), need.value, None)
+    assert rc == -1 and b"aligned" in L.asr_last_error()
+    base = (ws.data_ptr() + 255) // 256 * 256
+    rc = L.asr_solve_batched(arr, n, copies.data_ptr(), a32.ctypes.data_as(fp), s32.ctypes.data_as(fp), None, 1, 3, 16, 16, 64, 64,
+                             x.data_ptr(), None, base + 16, need.value, None)
+    assert rc == -1 and b"aligned" in L.asr_last_error()
