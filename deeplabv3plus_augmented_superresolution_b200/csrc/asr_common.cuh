@@ -137,6 +137,18 @@ __device__ __forceinline__ unsigned tap_offset(unsigned raw_x, unsigned raw_y, u
         : "=r"(o) : "r"(raw_x), "r"(raw_y), "r"(cst4), "n"(4 * STRIDE));
     return o;
 }
+// The same address for two pixels at once on the FMA pipe (one issue slot per pixel instead of two integer ones):
+// 4*STRIDE*fy + 4*fx + cst evaluated in units of 2^-149, i.e. on fp32 DENORMALS, whose bit pattern is the integer
+// itself.  fx, fy are the float floors the gather has anyway; every product and partial sum is an integer below
+// 2^23 in those units, so both fmas are exact (this is address arithmetic, not part of the op sequence; without
+// -ftz the FMA pipe handles denormals at full rate).  Needs |coordinate| * 4 * STRIDE < 2^23: check_shapes limits
+// the canvas to 16384 pixels per side.
+__device__ __forceinline__ float denorm_int(int c) { return (c >= 0) ? __uint_as_float((unsigned)c) : -__uint_as_float((unsigned)(-c)); }
+template <int STRIDE>
+__device__ __forceinline__ f32x2 tap_addr2(f32x2 fxf, f32x2 fyf, f32x2 cst_d) {
+    const float k4 = __uint_as_float(4u), ks = __uint_as_float(4u * STRIDE);
+    return fma2(fyf, pk(ks, ks), fma2(fxf, pk(k4, k4), cst_d));
+}
 // ld.shared of one tap: 32-bit shared address + immediate byte offset
 template <int OFF>
 __device__ __forceinline__ float lds_tap(unsigned addr) {

@@ -14,6 +14,7 @@
 // TensorFlow ops (see asr_common.cuh).  DESIGN.md derives the restructurings used here and why
 // each is bit-identical to the literal two-pass evaluation.
 #include <cuda.h>
+#include <limits.h>
 #include <math.h>
 #include <stdlib.h>
 #include <vector>
@@ -76,27 +77,35 @@ __global__ void k_init_upsample(const float* __restrict__ copies, const ImgParam
 // For copy k and LR cell (i,j):  r = resize(translate(rotate(x)))[i,j] - y_k[i,j].
 // The resize reads only z at rows {4i+1,4i+2} x cols {4j+1,4j+2}; each z is a 2x2 stencil of the
 // rotated image p on integer positions, so one cell needs p on a 3x3 patch whose origin is
-// (4j+1+floor(-dx), 4i+1+floor(-dy)).  A CTA (16x12 cells, one copy) bounds the x region those
-// patches can touch from the four corner coordinates, pulls that box into shared memory with ONE
-// TMA tensor load (cp.async.bulk.tensor; out-of-image elements arrive as zeros, which is exactly the
-// op's fill), evaluates the 48x36 needed p values with the op's arithmetic, and a second phase
-// combines them per cell with per-column/row tap tables that carry the literal translate weights,
-// the zero fill of p outside the canvas, and the rounding case floor(fl(Z-dx)) == Z+floor(-dx)+1.
+// (4j+1+floor(-dx), 4i+1+floor(-dy)).  A CTA (16x12 cells, one copy) pulls the x region those patches can
+// touch into shared memory with ONE TMA tensor load (cp.async.bulk.tensor; out-of-image elements arrive as
+// zeros, which is exactly the op's fill), evaluates the 48x36 needed p values with the op's arithmetic, and
+// a second phase combines them per cell with per-column/row tap tables that carry the literal translate
+// weights, the zero fill of p outside the canvas, and the rounding case floor(fl(Z-dx)) == Z+floor(-dx)+1.
+// Everything that depends on the transforms only -- the box origin of every (tile, copy) and the tap tables of
+// every copy -- is computed ONCE per solve by k_forward_tables, so the per-iteration CTA starts with one 8-byte
+// descriptor load and the TMA issue (round 1 recomputed boxes and tables in every CTA of every iteration:
+// half of the kernel's instructions).
 constexpr int K1_TJ = 16;              // LR tile: 16 cells wide ...
 constexpr int K1_TI = 12;              // ... 12 cells tall = 192 cells, one per thread in the second phase
 constexpr int K1_THREADS = 192;        // 48 p-columns x 4 row groups of 9 rows
 constexpr int K1_PC = 3 * K1_TJ;       // needed p columns (48) and rows (36) per tile
 constexpr int K1_PR = 3 * K1_TI;
-constexpr int K1_PBS = K1_PC + 1;      // p buffer stride
-constexpr int K1_RPS = 10;             // row-product table stride per row group (9 rows, padded to keep pairs 8-byte aligned)
+constexpr int K1_PBS = K1_PC;          // p buffer stride 48: 3 rows = 144 = 16 (mod 32) floats, so the two cell rows a warp reads in
+                                       // the second phase land on complementary bank sets (stride 49 collided on one bank: 2 wavefronts per load)
 constexpr int K1_XS = 96;              // TMA box width (floats): 62*sqrt(2)+2+3 < 96, multiple of 32 (a pitch of 80 = 16 mod 32 saves TMA
                                        // bytes for small rotations but adds conflicts across source rows: measured 29.5 vs 28.0 us)
 constexpr int K1_XR_SMALL = 60;        // TMA box height when 62|sin|+46|cos|+3 <= 60 for every copy (|angle| <~ 0.19 rad): 7 CTAs/SM
 constexpr int K1_XR_BIG = 84;          // ... for any rotation: sqrt(62^2+46^2)+3 < 84: 5 CTAs/SM
+constexpr int K1_SPAN_X = 4 * (K1_TJ - 1) + 2, K1_SPAN_Y = 4 * (K1_TI - 1) + 2;   // last needed p position = first + SPAN
+constexpr int K1_EMPTY = INT_MIN;      // BoxDesc.by0 of a (tile, copy) whose rotated image is all zero
 template <int XR>
 constexpr size_t k1_smem() {
-    return sizeof(float) * K1_XS * XR + sizeof(float) * (K1_PR * K1_PBS) + sizeof(float4) * (K1_TJ + K1_TI) + sizeof(float) * 2 * 4 * K1_RPS + 16;
+    return sizeof(float) * K1_XS * XR + sizeof(float) * (K1_PR * K1_PBS) + 16;
 }
+// per kept copy, device-side: rotate coefficients, floor of the translate offsets, index of the LR map y_k in `copies`
+struct __align__(16) FwdCopy { float r0, r1, r2, r3, r4, r5; int sx, sy; int ysrc, pad0, pad1, pad2; };
+typedef int2 BoxDesc;                  // x = TMA box start column (multiple of 4), y = start row or K1_EMPTY
 
 // translate stencil weights of z-column Z on the window (Z+s, Z+s+1), validity of p folded in
 __device__ __forceinline__ float2 translate_taps(int Z, float t, int s, int limit) {
@@ -111,106 +120,126 @@ __device__ __forceinline__ float2 translate_taps(int Z, float t, int s, int limi
     return make_float2(wa, wb);
 }
 
+// Once per solve: for every kept copy the forward tap tables (one float4 per LR column and per LR row), the
+// compact per-copy record, and for every (LR tile, copy) the origin of the x box its taps can touch.
+// blockIdx.x < tile_blocks: one thread per tile of the copy; then one thread per LR column / row.
+__global__ void k_forward_tables(const FwdXf* __restrict__ fwd, const int* __restrict__ src_idx, const ImgParams* __restrict__ ip,
+                                 FwdCopy* __restrict__ fcp, float4* __restrict__ fcolw, float4* __restrict__ froww,
+                                 BoxDesc* __restrict__ boxd, int N, int h, int w, int H, int W, int ntj, int nti, int box_rows) {
+    const int ks = blockIdx.y, b = blockIdx.z;
+    if (ks >= ip[b].n_kept) return;
+    const size_t slot = (size_t)b * N + ks;
+    const FwdXf T = fwd[slot];
+    const int sx = (int)floorf(T.tx), sy = (int)floorf(T.ty);
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    const int t1 = ntj * nti;
+    if (e == 0) fcp[slot] = FwdCopy{T.r0, T.r1, T.r2, T.r3, T.r4, T.r5, sx, sy, ip[b].stack * N + src_idx[slot], 0, 0, 0};
+    if (e < t1) {
+        // source bounding box of the tile's p region.  Each rounded op of the coordinate is monotone in qx and in qy,
+        // so the literal coordinates of the four corners bound every tap.
+        const int ti = e / ntj, tj = e - ti * ntj;
+        const int qx_lo = 4 * tj * K1_TJ + 1 + sx, qy_lo = 4 * ti * K1_TI + 1 + sy;
+        float xmin = INFINITY, xmax = -INFINITY, ymin = INFINITY, ymax = -INFINITY;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            const float qx = (float)(qx_lo + ((c & 1) ? K1_SPAN_X : 0)), qy = (float)(qy_lo + ((c & 2) ? K1_SPAN_Y : 0));
+            const float cix = affine_coord(T.r0, qx, T.r1, qy, T.r2), ciy = affine_coord(T.r3, qx, T.r4, qy, T.r5);
+            xmin = fminf(xmin, cix); xmax = fmaxf(xmax, cix); ymin = fminf(ymin, ciy); ymax = fmaxf(ymax, ciy);
+        }
+        const int bx0 = (int)floorf(xmin), bx1 = (int)floorf(xmax) + 1, by0 = (int)floorf(ymin), by1 = (int)floorf(ymax) + 1;
+        // TMA needs the innermost start coordinate 16-byte aligned (an unaligned start faults with
+        // "illegal instruction" on B200: scripts/dev/tma_test3.cu), so the box starts at bx0 rounded down to 4
+        const int bx0a = bx0 & ~3;
+        const bool empty = (bx1 < 0 || bx0 >= W || by1 < 0 || by0 >= H);   // the rotated image is all zero here
+        // the host picks the box variant from the same transforms (build_tables): a box that does not fit is a bug, not data
+        if (!empty && (bx1 - bx0a >= K1_XS || by1 - by0 >= box_rows)) __trap();
+        boxd[slot * t1 + e] = make_int2(bx0a, empty ? K1_EMPTY : by0);
+    }
+    const int c = e - t1;
+    if (c >= 0 && c < w) {
+        const int Z1 = 4 * c + 1;
+        const float2 a = translate_taps(Z1, T.tx, sx, W), d = translate_taps(Z1 + 1, T.tx, sx, W);
+        fcolw[slot * w + c] = make_float4(a.x, a.y, d.x, d.y);
+    } else if (c >= w && c < w + h) {
+        const int r = c - w, Z1 = 4 * r + 1;
+        const float2 a = translate_taps(Z1, T.ty, sy, H), d = translate_taps(Z1 + 1, T.ty, sy, H);
+        froww[slot * h + r] = make_float4(a.x, a.y, d.x, d.y);
+    }
+}
+
 template <int XR>
 __global__ void __launch_bounds__(K1_THREADS)
 k_forward_residual(const __grid_constant__ CUtensorMap xmap, const float* __restrict__ copies, float* __restrict__ resid,
-                   const FwdXf* __restrict__ fwd, const int* __restrict__ src_idx,
-                   const ImgParams* __restrict__ ip, int it, int N, int h, int w, int wp, int H, int W, int ntj, unsigned ntj_magic,
-                   int b_base) {
+                   const FwdCopy* __restrict__ fcp, const float4* __restrict__ fcolw, const float4* __restrict__ froww,
+                   const BoxDesc* __restrict__ boxd, const ImgParams* __restrict__ ip, int it, int check_ip, int N, int h, int w, int wp,
+                   int ntj, unsigned ntj_magic, int b_base) {
+    // block = (48 p-columns, 4 row groups); the linear id maps to one LR cell in the second phase
     const int b = blockIdx.z, ks = blockIdx.y;
-    const ImgParams P = ip[b];
-    if (ks >= P.n_kept || it >= P.num_iter) return;
+    if (check_ip && (ks >= ip[b].n_kept || it >= ip[b].num_iter)) return;   // host clears check_ip when every image of the launch is live
 
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ __align__(8) unsigned long long bar;
     float* xt = reinterpret_cast<float*>(smem_raw);                              // [XR][K1_XS], filled by TMA
     float* pb = xt + K1_XS * XR;                                                 // [K1_PR][K1_PBS]
-    float4* colw = reinterpret_cast<float4*>(pb + K1_PR * K1_PBS);               // [K1_TJ] (w1a,w1b,w2a,w2b)
-    float4* roww = colw + K1_TJ;                                                 // [K1_TI]
-    float* rpx = reinterpret_cast<float*>(roww + K1_TI);                         // [4][K1_RPS] fl(r1*qy) per needed p row
-    float* rpy = rpx + 4 * K1_RPS;                                               // [4][K1_RPS] fl(r4*qy)
-    int* boxs = reinterpret_cast<int*>(rpy + 4 * K1_RPS);                        // bx0a, by0, empty
+    int* boxs = reinterpret_cast<int*>(pb + K1_PR * K1_PBS);                     // bx0a, by0
 
-    const int tid = threadIdx.x, lane = tid & 31;
+    const int pcn = threadIdx.x, g = threadIdx.y;                                // p column, row group (9 rows = 3 cell rows each)
+    const int tid = g * K1_PC + pcn;
+    const unsigned slot = (unsigned)b * (unsigned)N + (unsigned)ks;              // B*N*max(h,w,tiles) < 2^32 is checked on the host
+    if (tid == 0) {
+        const BoxDesc d = boxd[(size_t)slot * gridDim.x + blockIdx.x];
+        boxs[0] = d.x; boxs[1] = d.y;
+        mbar_init(&bar, 1);
+        if (d.y != K1_EMPTY) tma_load_3d(xt, &xmap, d.x, d.y, b_base + b, &bar, (unsigned)(K1_XS * XR * sizeof(float)));
+    }
     const int ti = (ntj == 1) ? (int)blockIdx.x : (int)__umulhi(blockIdx.x, ntj_magic);          // tile row (2^32/1 does not fit the magic)
     const int tj = (int)blockIdx.x - ti * ntj;                                                    // tile column
     const int j0 = tj * K1_TJ, i0 = ti * K1_TI;
-    const FwdXf T = fwd[(size_t)b * N + ks];
-    const int sx = (int)floorf(T.tx), sy = (int)floorf(T.ty);
-    const int qx_lo = 4 * j0 + 1 + sx, qy_lo = 4 * i0 + 1 + sy;   // first needed p position
-    constexpr int SPAN_X = 4 * (K1_TJ - 1) + 2, SPAN_Y = 4 * (K1_TI - 1) + 2;   // last needed = lo + SPAN
-
-    if (tid < 32) {
-        // ---- warp 0: source bounding box of the p region.  Each rounded op of the coordinate is monotone
-        //      in qx and in qy, so the literal coordinates of the four corners bound every tap. -------------
-        const float qx = (float)(qx_lo + ((lane & 1) ? SPAN_X : 0)), qy = (float)(qy_lo + ((lane & 2) ? SPAN_Y : 0));
-        const float cix = affine_coord(T.r0, qx, T.r1, qy, T.r2), ciy = affine_coord(T.r3, qx, T.r4, qy, T.r5);
-        const int bx0 = (int)floorf(warp_min(cix)), bx1 = (int)floorf(warp_max(cix)) + 1;
-        const int by0 = (int)floorf(warp_min(ciy)), by1 = (int)floorf(warp_max(ciy)) + 1;
-        // TMA needs the innermost start coordinate 16-byte aligned (an unaligned start faults with
-        // "illegal instruction" on B200: scripts/dev/tma_test3.cu), so the box starts at bx0 rounded down to 4
-        const int bx0a = bx0 & ~3;
-        // empty: the rotated image is all zero here
-        const int empty = (bx1 < 0 || bx0 >= W || by1 < 0 || by0 >= H);
-        // the host picks the box variant from the same transforms (build_tables): a box that does not fit is a bug, not data
-        if (!empty && (bx1 - bx0a >= K1_XS || by1 - by0 >= XR)) __trap();
-        if (lane == 0) {
-            boxs[0] = bx0a; boxs[1] = by0; boxs[2] = empty;
-            mbar_init(&bar, 1);
-            if (!empty) tma_load_3d(xt, &xmap, bx0a, by0, b_base + b, &bar, (unsigned)(K1_XS * XR * sizeof(float)));
-        }
-    } else if (tid >= 64 && tid < 64 + K1_TJ) {
-        // ---- tap tables, overlapped with the TMA flight -------------------------------------------------------
-        const int c = tid - 64, Z1 = 4 * (j0 + c) + 1;
-        const float2 a = translate_taps(Z1, T.tx, sx, W), d = translate_taps(Z1 + 1, T.tx, sx, W);
-        colw[c] = make_float4(a.x, a.y, d.x, d.y);
-    } else if (tid >= 96 && tid < 96 + K1_TI) {
-        const int c = tid - 96, Z1 = 4 * (i0 + c) + 1;
-        const float2 a = translate_taps(Z1, T.ty, sy, H), d = translate_taps(Z1 + 1, T.ty, sy, H);
-        roww[c] = make_float4(a.x, a.y, d.x, d.y);
-    } else if (tid >= 128 && tid < 128 + K1_PR) {
-        // the row products of the rotate coordinates, one per needed p row
-        const int m = tid - 128, gg = m / 9, mm = m - 9 * gg;
-        const float qyf = (float)(qy_lo + 12 * gg + 4 * (mm / 3) + (mm % 3));
-        rpx[gg * K1_RPS + mm] = fmul(T.r1, qyf);
-        rpy[gg * K1_RPS + mm] = fmul(T.r4, qyf);
-    }
-    // this thread's cell of the second phase: request its LR sample now, it is consumed at the very end
+    const FwdCopy T = fcp[slot];
+    const int qx_lo = 4 * j0 + 1 + T.sx, qy_lo = 4 * i0 + 1 + T.sy;   // first needed p position
+    // this thread's cell of the second phase: request its LR sample and tap weights now, they are consumed at the very end
     const int ci = tid / K1_TJ, cj = tid % K1_TJ;
     const int i = i0 + ci, j = j0 + cj;
     float yk = 0.0f;
-    if (i < h && j < w) yk = __ldg(copies + (((size_t)P.stack * N + src_idx[(size_t)b * N + ks]) * h + i) * w + j);
-    __syncthreads();   // box, barrier init and tables visible
-    const bool empty = boxs[2] != 0;
+    float4 wc = make_float4(0.f, 0.f, 0.f, 0.f), wr = wc;
+    const bool live = i < h && j < w;
+    if (live) {
+        yk = __ldg(copies + (size_t)T.ysrc * (unsigned)(h * w) + (unsigned)(i * w + j));
+        wc = __ldg(fcolw + (slot * (unsigned)w + (unsigned)j));
+        wr = __ldg(froww + (slot * (unsigned)h + (unsigned)i));
+    }
+    __syncthreads();   // box origin and barrier init visible
+    const bool empty = boxs[1] == K1_EMPTY;
 
     if (!empty) {
         // ---- p = rotate-gather of x at the needed integer positions ------------------------------
-        const int pcn = tid % K1_PC, g = tid / K1_PC;             // p column, row group (9 rows = 3 cell rows each)
-        const float qxf = (float)(qx_lo + 4 * (pcn / 3) + (pcn % 3));
+        const float qxf = (float)(qx_lo + pcn + pcn / 3);         // 4*(pcn/3) + pcn%3
+        const float qy0 = (float)(qy_lo + 12 * g);                // first row of the group; rows qy0 + {0,1,2,4,5,6,8,9,10}
         const float ax = fmul(T.r0, qxf), ay = fmul(T.r3, qxf);
-        // byte offset of tap (y0,x0) = 4*(raw_y*XS + raw_x + cst) (mod 2^32); kept opaque so that the compiler
-        // cannot split the magic constant out of it and re-add it once per tap
-        unsigned cst = ((0u - (unsigned)(kMagicBits + boxs[1]) * K1_XS - (unsigned)(kMagicBits + boxs[0])) << 2) + smem_u32(xt);
-        asm volatile("" : "+r"(cst));
+        // byte address of tap (y0,x0) = 4*(y0*XS + x0) + cst, box origin and tile address folded into cst
+        const int cst = (int)smem_u32(xt) - 4 * (boxs[1] * K1_XS + boxs[0]);
+        const float cstf = denorm_int(cst);
+        const f32x2 cstd = pk(cstf, cstf);
         float* prow = pb + (9 * g) * K1_PBS + pcn;
         const f32x2 axp = pk(ax, ax), ayp = pk(ay, ay), r2p = pk(T.r2, T.r2), r5p = pk(T.r5, T.r5);
+        const f32x2 r1p = pk(T.r1, T.r1), r4p = pk(T.r4, T.r4), qy0p = pk(qy0, qy0);
         const f32x2 magic2 = pk(kMagic, kMagic), one2 = pk(1.0f, 1.0f);
-        const float* rx = rpx + g * K1_RPS;
-        const float* ry = rpy + g * K1_RPS;
         mbar_wait(&bar, 0);
-        // rows (m, m+1) of the column travel as the two lanes of packed fp32 instructions (asr_common.cuh)
+        // two rows of the column travel as the two lanes of packed fp32 instructions (asr_common.cuh); the row
+        // coordinates are small integers, so qy0 + offset is exact and equals the literal (float)qy
 #pragma unroll
         for (int m = 0; m < 8; m += 2) {
-            const f32x2 ix = add2(add2(axp, *reinterpret_cast<const f32x2*>(rx + m)), r2p);
-            const f32x2 iy = add2(add2(ayp, *reinterpret_cast<const f32x2*>(ry + m)), r5p);
-            const f32x2 tx = add2_rd(ix, magic2), ty = add2_rd(iy, magic2);
-            const f32x2 fxf = sub2(tx, magic2), fyf = sub2(ty, magic2);
+            const int o0 = 4 * (m / 3) + m % 3, o1 = 4 * ((m + 1) / 3) + (m + 1) % 3;
+            const f32x2 qy2 = add2(qy0p, pk((float)o0, (float)o1));
+            const f32x2 ix = add2(sum2(axp, mul2(r1p, qy2)), r2p);      // fl(fl(fl(r0*qx) + fl(r1*qy)) + r2)
+            const f32x2 iy = add2(sum2(ayp, mul2(r4p, qy2)), r5p);
+            const f32x2 fxf = sub2(add2_rd(ix, magic2), magic2), fyf = sub2(add2_rd(iy, magic2), magic2);   // floors
             // (x_ceil - x) == 1 - (x - x_floor) bit for bit unless x in (-1,0), where that weight only ever
             // multiplies the out-of-image tap x_floor = -1, i.e. an exact zero
             const f32x2 wx1 = sub2(ix, fxf), wx0 = sub2(one2, wx1);
             const f32x2 wy1 = sub2(iy, fyf), wy0 = sub2(one2, wy1);
-            const unsigned ta = tap_offset<K1_XS>(__float_as_uint(pk_lo(tx)), __float_as_uint(pk_lo(ty)), cst);
-            const unsigned tb = tap_offset<K1_XS>(__float_as_uint(pk_hi(tx)), __float_as_uint(pk_hi(ty)), cst);
+            const f32x2 tp = tap_addr2<K1_XS>(fxf, fyf, cstd);
+            const unsigned ta = (unsigned)tp, tb = (unsigned)(tp >> 32);
             const f32x2 o = bilerp2(pk(lds_tap<0>(ta), lds_tap<0>(tb)), pk(lds_tap<4>(ta), lds_tap<4>(tb)),
                                     pk(lds_tap<4 * K1_XS>(ta), lds_tap<4 * K1_XS>(tb)),
                                     pk(lds_tap<4 * K1_XS + 4>(ta), lds_tap<4 * K1_XS + 4>(tb)), wx0, wx1, wy0, wy1);
@@ -218,21 +247,21 @@ k_forward_residual(const __grid_constant__ CUtensorMap xmap, const float* __rest
             prow[(m + 1) * K1_PBS] = pk_hi(o);
         }
         {   // the ninth row
-            const float ix = fadd(fadd(ax, rx[8]), T.r2), iy = fadd(fadd(ay, ry[8]), T.r5);
+            const float qy = fadd(qy0, 10.0f);
+            const float ix = fadd(fadd(ax, fmul(T.r1, qy)), T.r2), iy = fadd(fadd(ay, fmul(T.r4, qy)), T.r5);
             const Floor fx = floor_magic(ix), fy = floor_magic(iy);
             const float wx1 = fsub(ix, fx.f), wx0 = fsub(1.0f, wx1);
             const float wy1 = fsub(iy, fy.f), wy0 = fsub(1.0f, wy1);
-            const unsigned t0 = tap_offset<K1_XS>((unsigned)fx.raw, (unsigned)fy.raw, cst);
+            const unsigned t0 = (unsigned)cst + 4u * ((unsigned)(fy.raw - kMagicBits) * K1_XS + (unsigned)(fx.raw - kMagicBits));
             prow[8 * K1_PBS] = bilerp(lds_tap<0>(t0), lds_tap<4>(t0), lds_tap<4 * K1_XS>(t0), lds_tap<4 * K1_XS + 4>(t0), wx0, wx1, wy0, wy1);
         }
     }
     __syncthreads();
 
     // ---- one cell per thread: translate (2x2 z values), resize (literal lerps at 0.5), minus y ---------
-    if (i < h && j < w) {
+    if (live) {
         float D = 0.0f;
         if (!empty) {
-            const float4 wc = colw[cj], wr = roww[ci];
             float Tx[3][2];
 #pragma unroll
             for (int bb = 0; bb < 3; ++bb) {
@@ -249,7 +278,7 @@ k_forward_residual(const __grid_constant__ CUtensorMap xmap, const float* __rest
             const float bot = fadd(bl, fmul(fsub(br, bl), 0.5f));
             D = fadd(top, fmul(fsub(bot, top), 0.5f));
         }
-        resid[(((size_t)b * N + ks) * h + i) * wp + j] = fsub(D, yk);
+        resid[(size_t)slot * (unsigned)(h * wp) + (unsigned)(i * wp + j)] = fsub(D, yk);
     }
 }
 
@@ -287,7 +316,7 @@ template <int TY> struct K2Rows { static constexpr int value = TY == 64 ? 96 : 8
 constexpr int K2_CHUNK = 128;          // copies whose boxes/transforms are staged at once
 enum { BAR_EMPTY = 1 };   // named barriers 1,2 (0 is __syncthreads)
 struct __align__(16) KBox {
-    unsigned cst;   // word offset folding the magic bias and the box origin (mod 2^32), buffer offset excluded
+    int cst;        // word offset of the box origin inside a u buffer: -(qy_lo*US + qx_lo), buffer offset excluded
     int cbx0, cby0; // first LR cell of the box
     int ncxy;       // ncx | ncy << 8 | skip << 16   (skip: box does not touch the LR grid, u == 0)
     int qx_lo, qy_lo;
@@ -417,7 +446,7 @@ k_gradient_update(const __grid_constant__ CUtensorMap rmap, const float* __restr
             if (!skip && (4 * ncx > K2_US || 4 * ncy > K2_UR)) __trap();
             bx.ncxy = (ncx & 0xff) | ((ncy & 0xff) << 8) | (skip << 16);
             if (skip) { bx.cbx0 = 0; bx.cby0 = 0; }   // its (unused) staging copies stay inside the tables
-            bx.cst = 0u - (unsigned)(kMagicBits + bx.qy_lo) * K2_US - (unsigned)(kMagicBits + bx.qx_lo);
+            bx.cst = -(bx.qy_lo * K2_US + bx.qx_lo);
             bx.inv_ncx = (65536 + ncx - 1) / max(ncx, 1);
             bx.pad = 0;
             boxes[tid] = bx;
@@ -432,9 +461,11 @@ k_gradient_update(const __grid_constant__ CUtensorMap rmap, const float* __restr
                 const KBox bx = boxes[kc];
                 if (!(bx.ncxy >> 16)) {
                     const InvXf T = xfs[kc];
-                    // byte offset of tap (y0,x0) = 4*(raw_y*US + raw_x + cst) (mod 2^32)
-                    unsigned cst = ((bx.cst + (unsigned)((kc & 1) * (K2_US * K2_UR))) << 2) + smem_u32(ut);
+                    // byte address of tap (y0,x0) = 4*(y0*US + x0) + cst: box origin, buffer and tile address folded into cst
+                    int cst = 4 * (bx.cst + (kc & 1) * (K2_US * K2_UR)) + (int)smem_u32(ut);
                     asm volatile("" : "+r"(cst));   // opaque and ordered after the wait above: no tap load can be hoisted over it
+                    const float cstf = denorm_int(cst);
+                    const f32x2 cstd = pk(cstf, cstf);
                     const f32x2 b2p = pk(T.b2, T.b2), b5p = pk(T.b5, T.b5);
                     // products stay scalar (a packed product feeding a packed sum would be contracted, asr_common.cuh)
                     const f32x2 axp = pk(fmul(T.b0, X0f), fmul(T.b0, X1f)), ayp = pk(fmul(T.b3, X0f), fmul(T.b3, X1f));
@@ -444,15 +475,14 @@ k_gradient_update(const __grid_constant__ CUtensorMap rmap, const float* __restr
                         const float bxr = rp.x, byr = rp.y;
                         const f32x2 ix = add2(add2(axp, pk(bxr, bxr)), b2p);
                         const f32x2 iy = add2(add2(ayp, pk(byr, byr)), b5p);
-                        // floor_magic on both lanes: raw bits = kMagicBits + floor, float floor = raw - magic
-                        const f32x2 tx = add2_rd(ix, magic2), ty = add2_rd(iy, magic2);
-                        const f32x2 fxf = sub2(tx, magic2), fyf = sub2(ty, magic2);
+                        // floor on both lanes: fl_rd(v + 1.5*2^23) - 1.5*2^23
+                        const f32x2 fxf = sub2(add2_rd(ix, magic2), magic2), fyf = sub2(add2_rd(iy, magic2), magic2);
                         // (x_ceil - x) == 1 - (x - x_floor) bit for bit unless x in (-1,0), where that weight only
                         // multiplies the tap x_floor = -1, which lies outside the canvas and is an exact zero of u
                         const f32x2 wx1 = sub2(ix, fxf), wx0 = sub2(one2, wx1);
                         const f32x2 wy1 = sub2(iy, fyf), wy0 = sub2(one2, wy1);
-                        const unsigned ta = tap_offset<K2_US>(__float_as_uint(pk_lo(tx)), __float_as_uint(pk_lo(ty)), cst);
-                        const unsigned tb = tap_offset<K2_US>(__float_as_uint(pk_hi(tx)), __float_as_uint(pk_hi(ty)), cst);
+                        const f32x2 tp = tap_addr2<K2_US>(fxf, fyf, cstd);
+                        const unsigned ta = (unsigned)tp, tb = (unsigned)(tp >> 32);
                         accp[r] = add2(accp[r], bilerp2(pk(lds_tap<0>(ta), lds_tap<0>(tb)), pk(lds_tap<4>(ta), lds_tap<4>(tb)),
                                                         pk(lds_tap<4 * K2_US>(ta), lds_tap<4 * K2_US>(tb)),
                                                         pk(lds_tap<4 * K2_US + 4>(ta), lds_tap<4 * K2_US + 4>(tb)), wx0, wx1, wy0, wy1));
@@ -706,8 +736,10 @@ static size_t align_up(size_t v, size_t a = 256) { return (v + a - 1) / a * a; }
 static int pitch4(int w) { return (w + 3) & ~3; }   // residual row pitch: TMA strides must be multiples of 16 bytes
 
 struct Layout {
-    size_t xa, xb, s0, s1, s2, resid, tapc, tapr, fwd, inv, src, ip, hp, sched, accum, total;
+    size_t xa, xb, s0, s1, s2, resid, tapc, tapr, fwd, inv, src, ip, hp, sched, accum, fcp, fcolw, froww, boxd, total;
 };
+static int k1_tiles_x(int w) { return (w + K1_TJ - 1) / K1_TJ; }
+static int k1_tiles_y(int h) { return (h + K1_TI - 1) / K1_TI; }
 
 static Layout make_layout(int B, int N, int h, int w, int H, int W, int max_iter) {
     Layout L;
@@ -728,6 +760,10 @@ static Layout make_layout(int B, int N, int h, int w, int H, int W, int max_iter
     L.hp = o; o += align_up(sizeof(AsrSolveParams) * (size_t)B);
     L.sched = o; o += align_up(sizeof(Sched) * (size_t)B * (size_t)(max_iter > 0 ? max_iter : 1));
     L.accum = o; o += align_up(sizeof(double) * 4 * (size_t)B);
+    L.fcp = o; o += align_up(sizeof(FwdCopy) * (size_t)B * N);
+    L.fcolw = o; o += align_up(sizeof(float4) * (size_t)B * N * w);
+    L.froww = o; o += align_up(sizeof(float4) * (size_t)B * N * h);
+    L.boxd = o; o += align_up(sizeof(BoxDesc) * (size_t)B * N * k1_tiles_x(w) * k1_tiles_y(h));
     L.total = o;
     return L;
 }
@@ -737,7 +773,9 @@ static int check_shapes(int B, int N, int h, int w, int H, int W) {
     if (H != 4 * h || W != 4 * w)
         return fail(ASR_EUNSUPPORTED, "only output_size == 4 * feature_size is implemented (got %dx%d -> %dx%d)", h, w, H, W);
     if (B > 65535 || N > 65535) return fail(ASR_EINVAL, "B and N must be <= 65535");
-    if (H > (1 << 20) || W > (1 << 20)) return fail(ASR_EINVAL, "image too large for the fp32 floor trick");
+    if (H > 16384 || W > 16384) return fail(ASR_EINVAL, "output larger than 16384 pixels per side (fp32 address arithmetic of the gathers)");
+    if ((double)B * N * (double)(h > w ? h : w) * 16.0 >= 4294967296.0 || (double)N * h * w >= 2147483648.0)
+        return fail(ASR_EINVAL, "B*N*max(h,w) must stay below 2^28 and N*h*w below 2^31 (32-bit table offsets)");
     return ASR_OK;
 }
 
@@ -838,6 +876,7 @@ struct Device {
     float *xa, *xb, *s0, *s1, *s2, *resid;
     float2 *tapc, *tapr;
     FwdXf* fwd; InvXf* inv; int* src; ImgParams* ip; AsrSolveParams* hp; Sched* sched; double* accum;
+    FwdCopy* fcp; float4* fcolw; float4* froww; BoxDesc* boxd;
 };
 
 static Device bind(void* ws, const Layout& L) {
@@ -850,6 +889,7 @@ static Device bind(void* ws, const Layout& L) {
     D.fwd = (FwdXf*)(p + L.fwd); D.inv = (InvXf*)(p + L.inv); D.src = (int*)(p + L.src);
     D.ip = (ImgParams*)(p + L.ip); D.hp = (AsrSolveParams*)(p + L.hp); D.sched = (Sched*)(p + L.sched);
     D.accum = (double*)(p + L.accum);
+    D.fcp = (FwdCopy*)(p + L.fcp); D.fcolw = (float4*)(p + L.fcolw); D.froww = (float4*)(p + L.froww); D.boxd = (BoxDesc*)(p + L.boxd);
     return D;
 }
 
@@ -967,6 +1007,12 @@ static int k2_tile_height(int n_images, int H, int W) {
         }                                                                                                             \
     } while (0)
 
+#define ASR_LAUNCH_K1(small, t1, nk, nimg, st, ...)                                                                          \
+    do {                                                                                                                     \
+        if (small) ASR_LAUNCH_TIMED(0, k_forward_residual<K1_XR_SMALL>, dim3(t1, nk, nimg), dim3(K1_PC, K1_THREADS / K1_PC), k1_smem<K1_XR_SMALL>(), st, __VA_ARGS__); \
+        else ASR_LAUNCH_TIMED(0, k_forward_residual<K1_XR_BIG>, dim3(t1, nk, nimg), dim3(K1_PC, K1_THREADS / K1_PC), k1_smem<K1_XR_BIG>(), st, __VA_ARGS__);           \
+    } while (0)
+
 static int solve_impl(const AsrSolveParams* params, int n_params, const float* d_copies, const float* h_angles,
                       const float* h_shifts, const uint8_t* h_keep, const int32_t* h_stack_index, int B, int N, int h, int w,
                       int H, int W, float* d_x_out, float* d_loss_out, void* d_workspace, size_t workspace_bytes, void* stream) {
@@ -993,33 +1039,36 @@ static int solve_impl(const AsrSolveParams* params, int n_params, const float* d
             ASR_LAUNCH(k_fill, 64, 256, 0, st, D.s0 + (size_t)b * plane, T.hp[b].initial_accumulator_value, plane);
     ASR_LAUNCH(k_init_upsample, dim3((W + 31) / 32, (H + 7) / 8, B), dim3(32, 8), 0, st, d_copies, D.ip, D.xa, N, h, w, H, W);
 
-    const int ntj = (w + K1_TJ - 1) / K1_TJ;
-    const int t1 = ntj * ((h + K1_TI - 1) / K1_TI);
+    const int ntj = k1_tiles_x(w), nti = k1_tiles_y(h);
+    const int t1 = ntj * nti;
     CUtensorMap map_a, map_b, map_r;
     const int box_rows = T.small_box ? K1_XR_SMALL : K1_XR_BIG;
     const int wp = pitch4(w);
     if (int e = make_x_map(&map_a, D.xa, B, H, W, box_rows)) return e;
     if (int e = make_x_map(&map_b, D.xb, B, H, W, box_rows)) return e;
     if (int e = make_r_map(&map_r, D.resid, B * N, h, w)) return e;
+    // everything that depends on the transforms only, once per solve
     ASR_LAUNCH(k_tap_tables, dim3((4 * (w + h + 4 * K2_TPAD) + 255) / 256, N, B), 256, 0, st, D.inv, D.tapc, D.tapr, N, h, w, H, W);
+    ASR_LAUNCH(k_forward_tables, dim3((t1 + w + h + 127) / 128, T.max_kept, B), 128, 0, st, D.fwd, D.src, D.ip, D.fcp, D.fcolw, D.froww,
+               D.boxd, N, h, w, H, W, ntj, nti, box_rows);
     int group = params[0].images_in_flight > 0 ? params[0].images_in_flight : B;
     for (int b0 = 0; b0 < B; b0 += group) {
         const int nb = (B - b0 < group) ? B - b0 : group;
-        int iters = 0;
-        for (int b = b0; b < b0 + nb; ++b) iters = T.hp[b].num_iter > iters ? T.hp[b].num_iter : iters;
-        const size_t po = (size_t)b0 * plane, ro = (size_t)b0 * N * h * wp;
+        int iters = 0, min_iters = INT_MAX;
+        bool uniform_kept = true;   // every image of the group keeps max_kept copies: no CTA of the K1 grid is idle
+        for (int b = b0; b < b0 + nb; ++b) {
+            iters = T.hp[b].num_iter > iters ? T.hp[b].num_iter : iters;
+            min_iters = T.hp[b].num_iter < min_iters ? T.hp[b].num_iter : min_iters;
+            uniform_kept = uniform_kept && T.ip[b].n_kept == T.max_kept;
+        }
+        const size_t po = (size_t)b0 * plane, ro = (size_t)b0 * N * h * wp, so = (size_t)b0 * N;
         const int ty = k2_tile_height(nb, H, W);
         for (int it = 0; it < iters; ++it) {
             float* xc = ((it & 1) ? D.xb : D.xa) + po;
             float* xn = ((it & 1) ? D.xa : D.xb) + po;
-            if (T.small_box)
-                ASR_LAUNCH_TIMED(0, k_forward_residual<K1_XR_SMALL>, dim3(t1, T.max_kept, nb), K1_THREADS, k1_smem<K1_XR_SMALL>(), st,
-                    (it & 1) ? map_b : map_a, d_copies, D.resid + ro, D.fwd + (size_t)b0 * N, D.src + (size_t)b0 * N, D.ip + b0,
-                    it, N, h, w, wp, H, W, ntj, div_magic(ntj), b0);
-            else
-                ASR_LAUNCH_TIMED(0, k_forward_residual<K1_XR_BIG>, dim3(t1, T.max_kept, nb), K1_THREADS, k1_smem<K1_XR_BIG>(), st,
-                    (it & 1) ? map_b : map_a, d_copies, D.resid + ro, D.fwd + (size_t)b0 * N, D.src + (size_t)b0 * N, D.ip + b0,
-                    it, N, h, w, wp, H, W, ntj, div_magic(ntj), b0);
+            ASR_LAUNCH_K1(T.small_box, t1, T.max_kept, nb, st, (it & 1) ? map_b : map_a, d_copies, D.resid + ro, D.fcp + so, D.fcolw + so * w,
+                          D.froww + so * h, D.boxd + so * t1, D.ip + b0, it, (!uniform_kept || it >= min_iters) ? 1 : 0, N, h, w, wp, ntj,
+                          div_magic(ntj), b0);
             ASR_LAUNCH_K2(false, T.any_btv, ty, H, W, nb, st, map_r, xc, xn, D.s0 + po, D.s1 + po, D.s2 + po, D.tapc, D.tapr,
                           D.inv + (size_t)b0 * N, D.ip + b0, D.sched + b0, it, N, h, w, H, W, B, b0);
         }
@@ -1075,19 +1124,18 @@ extern "C" int asr_loss_grad_batched(const AsrSolveParams* params, int n_params,
 
     const size_t plane = (size_t)H * W;
     ASR_CUDA_TRY(cudaMemcpyAsync(D.xa, d_x, sizeof(float) * B * plane, cudaMemcpyDeviceToDevice, st));
-    const int ntj = (w + K1_TJ - 1) / K1_TJ;
-    const int t1 = ntj * ((h + K1_TI - 1) / K1_TI);
+    const int ntj = k1_tiles_x(w), nti = k1_tiles_y(h);
+    const int t1 = ntj * nti;
     CUtensorMap map_a, map_r;
     const int wp = pitch4(w);
-    if (int e = make_x_map(&map_a, D.xa, B, H, W, T.small_box ? K1_XR_SMALL : K1_XR_BIG)) return e;
+    const int box_rows = T.small_box ? K1_XR_SMALL : K1_XR_BIG;
+    if (int e = make_x_map(&map_a, D.xa, B, H, W, box_rows)) return e;
     if (int e = make_r_map(&map_r, D.resid, B * N, h, w)) return e;
     ASR_LAUNCH(k_tap_tables, dim3((4 * (w + h + 4 * K2_TPAD) + 255) / 256, N, B), 256, 0, st, D.inv, D.tapc, D.tapr, N, h, w, H, W);
-    if (T.small_box)
-        ASR_LAUNCH_TIMED(0, k_forward_residual<K1_XR_SMALL>, dim3(t1, T.max_kept, B), K1_THREADS, k1_smem<K1_XR_SMALL>(), st, map_a, d_copies,
-                         D.resid, D.fwd, D.src, D.ip, 0, N, h, w, wp, H, W, ntj, div_magic(ntj), 0);
-    else
-        ASR_LAUNCH_TIMED(0, k_forward_residual<K1_XR_BIG>, dim3(t1, T.max_kept, B), K1_THREADS, k1_smem<K1_XR_BIG>(), st, map_a, d_copies,
-                         D.resid, D.fwd, D.src, D.ip, 0, N, h, w, wp, H, W, ntj, div_magic(ntj), 0);
+    ASR_LAUNCH(k_forward_tables, dim3((t1 + w + h + 127) / 128, T.max_kept, B), 128, 0, st, D.fwd, D.src, D.ip, D.fcp, D.fcolw, D.froww,
+               D.boxd, N, h, w, H, W, ntj, nti, box_rows);
+    ASR_LAUNCH_K1(T.small_box, t1, T.max_kept, B, st, map_a, d_copies, D.resid, D.fcp, D.fcolw, D.froww, D.boxd, D.ip, 0, 1, N, h, w, wp, ntj,
+                  div_magic(ntj), 0);
     ASR_LAUNCH_K2(true, T.any_btv, k2_tile_height(B, H, W), H, W, B, st, map_r, D.xa, D.xb, D.s0, D.s1, D.s2, D.tapc, D.tapr, D.inv, D.ip,
                   D.sched, 0, N, h, w, H, W, B, 0);
     ASR_CUDA_TRY(cudaGetLastError());
