@@ -34,11 +34,12 @@ def needs_build() -> bool:
     return any(os.path.getmtime(f) > t for f in _deps())
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    if not force and not needs_build():
+def build(force: bool = False, verbose: bool = False, defines=(), out: str = LIB) -> str:
+    """`defines`/`out` build an experimental variant next to the product library (select it with ASR_LIB=<path>)."""
+    if not force and out == LIB and not needs_build():
         return LIB
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc, *NVCC_FLAGS, *( ["-Xptxas", "-v"] if verbose else []), "-o", LIB, *sources()]
+    cmd = [nvcc, *NVCC_FLAGS, *[f"-D{d}" for d in defines], *( ["-Xptxas", "-v"] if verbose else []), "-o", out, *sources()]
     env = dict(os.environ)
     env.pop("CC", None)   # the image exports CC=/opt/gcc/bin/gcc, which lacks libgomp specs; nvcc finds gcc on PATH
     env.pop("CXX", None)

@@ -13,7 +13,7 @@ from typing import Optional, Sequence
 import numpy as np
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG, "libasr.so")
+LIB_PATH = os.environ.get("ASR_LIB") or os.path.join(_PKG, "libasr.so")   # ASR_LIB: an experimental build (_build.build(defines=...))
 
 OPTIMIZERS = {"adam": 0, "sgd": 1, "adagrad": 2, "adadelta": 3, "adamax": 4}
 OPM_MODES = {"argmax": 0, "slice": 1, "slice_max": 2}

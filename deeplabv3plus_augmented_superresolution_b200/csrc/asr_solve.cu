@@ -167,13 +167,18 @@ __global__ void k_forward_tables(const FwdXf* __restrict__ fwd, const int* __res
     }
 }
 
-template <int XR>
+// Two thread maps for the gather phase (the second phase is always one cell per thread):
+//   CF = false  block (48, 4): thread = p column x group of 9 rows (4 packed row pairs + 1 scalar row).  32 consecutive needed
+//               columns span 42 source pixels (the resize reads 3 of every 4), so every tap load has 2-way bank conflicts.
+//   CF = true   block (32, 6): warp = half a p row (24 needed columns = 31 source pixels: conflict-free, 24 of 32 lanes
+//               active) x a third of the rows; thread = 12 rows = 6 packed pairs, no scalar row.  Same instruction count
+//               per CTA (fewer per-row instructions pay for the idle lanes), 37 % fewer shared-memory wavefronts.
+template <int XR, bool CF>
 __global__ void __launch_bounds__(K1_THREADS)
 k_forward_residual(const __grid_constant__ CUtensorMap xmap, const float* __restrict__ copies, float* __restrict__ resid,
                    const FwdCopy* __restrict__ fcp, const float4* __restrict__ fcolw, const float4* __restrict__ froww,
                    const BoxDesc* __restrict__ boxd, const ImgParams* __restrict__ ip, int it, int check_ip, int N, int h, int w, int wp,
                    int ntj, unsigned ntj_magic, int b_base) {
-    // block = (48 p-columns, 4 row groups); the linear id maps to one LR cell in the second phase
     const int b = blockIdx.z, ks = blockIdx.y;
     if (check_ip && (ks >= ip[b].n_kept || it >= ip[b].num_iter)) return;   // host clears check_ip when every image of the launch is live
 
@@ -183,8 +188,11 @@ k_forward_residual(const __grid_constant__ CUtensorMap xmap, const float* __rest
     float* pb = xt + K1_XS * XR;                                                 // [K1_PR][K1_PBS]
     int* boxs = reinterpret_cast<int*>(pb + K1_PR * K1_PBS);                     // bx0a, by0
 
-    const int pcn = threadIdx.x, g = threadIdx.y;                                // p column, row group (9 rows = 3 cell rows each)
-    const int tid = g * K1_PC + pcn;
+    // gather phase: p column, first p row, first q-row offset of this thread; the linear id maps to one LR cell in the second phase
+    const int pcn = CF ? 24 * (threadIdx.y & 1) + threadIdx.x : threadIdx.x;
+    const int prow0 = CF ? 12 * (threadIdx.y >> 1) : 9 * threadIdx.y, qrow0 = CF ? 16 * (threadIdx.y >> 1) : 12 * threadIdx.y;
+    const bool gathers = !CF || threadIdx.x < 24;
+    const int tid = threadIdx.y * blockDim.x + threadIdx.x;
     const unsigned slot = (unsigned)b * (unsigned)N + (unsigned)ks;              // B*N*max(h,w,tiles) < 2^32 is checked on the host
     if (tid == 0) {
         const BoxDesc d = boxd[(size_t)slot * gridDim.x + blockIdx.x];
@@ -211,16 +219,16 @@ k_forward_residual(const __grid_constant__ CUtensorMap xmap, const float* __rest
     __syncthreads();   // box origin and barrier init visible
     const bool empty = boxs[1] == K1_EMPTY;
 
-    if (!empty) {
+    if (!empty && gathers) {
         // ---- p = rotate-gather of x at the needed integer positions ------------------------------
         const float qxf = (float)(qx_lo + pcn + pcn / 3);         // 4*(pcn/3) + pcn%3
-        const float qy0 = (float)(qy_lo + 12 * g);                // first row of the group; rows qy0 + {0,1,2,4,5,6,8,9,10}
+        const float qy0 = (float)(qy_lo + qrow0);                 // first row of the thread; rows qy0 + {0,1,2,4,5,6,8,9,10,(12,13,14)}
         const float ax = fmul(T.r0, qxf), ay = fmul(T.r3, qxf);
         // byte address of tap (y0,x0) = 4*(y0*XS + x0) + cst, box origin and tile address folded into cst
         const int cst = (int)smem_u32(xt) - 4 * (boxs[1] * K1_XS + boxs[0]);
         const float cstf = denorm_int(cst);
         const f32x2 cstd = pk(cstf, cstf);
-        float* prow = pb + (9 * g) * K1_PBS + pcn;
+        float* prow = pb + prow0 * K1_PBS + pcn;
         const f32x2 axp = pk(ax, ax), ayp = pk(ay, ay), r2p = pk(T.r2, T.r2), r5p = pk(T.r5, T.r5);
         const f32x2 r1p = pk(T.r1, T.r1), r4p = pk(T.r4, T.r4), qy0p = pk(qy0, qy0);
         const f32x2 magic2 = pk(kMagic, kMagic), one2 = pk(1.0f, 1.0f);
@@ -228,7 +236,7 @@ k_forward_residual(const __grid_constant__ CUtensorMap xmap, const float* __rest
         // two rows of the column travel as the two lanes of packed fp32 instructions (asr_common.cuh); the row
         // coordinates are small integers, so qy0 + offset is exact and equals the literal (float)qy
 #pragma unroll
-        for (int m = 0; m < 8; m += 2) {
+        for (int m = 0; m < (CF ? 12 : 8); m += 2) {
             const int o0 = 4 * (m / 3) + m % 3, o1 = 4 * ((m + 1) / 3) + (m + 1) % 3;
             const f32x2 qy2 = add2(qy0p, pk((float)o0, (float)o1));
             const f32x2 ix = add2(sum2(axp, mul2(r1p, qy2)), r2p);      // fl(fl(fl(r0*qx) + fl(r1*qy)) + r2)
@@ -246,7 +254,7 @@ k_forward_residual(const __grid_constant__ CUtensorMap xmap, const float* __rest
             prow[m * K1_PBS] = pk_lo(o);
             prow[(m + 1) * K1_PBS] = pk_hi(o);
         }
-        {   // the ninth row
+        if (!CF) {   // the ninth row
             const float qy = fadd(qy0, 10.0f);
             const float ix = fadd(fadd(ax, fmul(T.r1, qy)), T.r2), iy = fadd(fadd(ay, fmul(T.r4, qy)), T.r5);
             const Floor fx = floor_magic(ix), fy = floor_magic(iy);
@@ -306,10 +314,25 @@ k_forward_residual(const __grid_constant__ CUtensorMap xmap, const float* __rest
 // memory (one thread per copy) before the roles split.
 constexpr int K2_T = 64;               // HR tile width; the tile height TY is 64 for batches that fill the GPU and 32 for one or two images
                                        // (one 512^2 image is only 64 tiles of 64x64: such a solve is latency-bound, 104 -> 79 us per iteration)
-constexpr int K2_GW = 8;               // gather warps; thread owns pixels (lane + 32c, warp + 8r), c<2, r<TY/8
+#ifndef ASR_K2_GW
+#define ASR_K2_GW 8
+#endif
+constexpr int K2_GW = ASR_K2_GW;       // gather warps; thread owns pixels (lane + 32c, warp + 8r), c<2, r<TY/8
 // fill warps: 4 in the throughput variant (64-row tiles, two CTAs per SM); 8 in the latency variant (32-row tiles, one lone CTA per
 // SM, where the fill warps' serial latency per copy is what the gather warps wait for)
-template <int TY> struct K2Fill { static constexpr int warps = TY == 64 ? 4 : 8, threads = 32 * (K2_GW + warps), ctas = TY == 64 ? 2 : 1; };
+#ifndef ASR_K2_FW64
+#define ASR_K2_FW64 8
+#endif
+#ifndef ASR_K2_AHEAD
+#define ASR_K2_AHEAD 3
+#endif
+template <int TY> struct K2Fill { static constexpr int warps = TY == 64 ? ASR_K2_FW64 : 8, threads = 32 * (K2_GW + warps), ctas = TY == 64 ? 2 : 1; };
+// Register split between the roles (setmaxnreg, per warpgroup of 4 warps): with 16 warps and two CTAs per SM the launch gives
+// every thread 64 registers; the fill warpgroups hand theirs back down to 40 and the gather warpgroups grow to 88, the
+// budget their 16 accumulators + 8-deep unrolled gather needs (8*88 + 8*40 = 16*64).
+constexpr bool K2_REG_SPLIT = (ASR_K2_FW64 == 8) && (K2_GW == 8);
+constexpr int K2_AHEAD = ASR_K2_AHEAD;   // copies the async staging (residual box + tap rows) runs ahead of the fill: the residuals of a big batch
+                                         // come from DRAM, two copies (~4000 clk) of lead left the fill waiting 320 clk per copy (clock64 trace)
 constexpr int K2_NG = 32 * K2_GW;
 constexpr int K2_US = 96;              // u tile stride: 64*sqrt(2)+2+3 < 96, multiple of 32
 template <int TY> struct K2Rows { static constexpr int value = TY == 64 ? 96 : 80; };   // u tile rows: sqrt(63^2+(TY-1)^2)+2 -> cells
@@ -374,6 +397,16 @@ __global__ void k_tap_tables(const InvXf* __restrict__ inv, float2* __restrict__
     }
 }
 
+#ifdef ASR_K2_TRACE   // development build only (scripts/dev/k2_trace.py): clock64 stamps of one CTA's hand-offs
+__device__ long long g_k2_trace[16][128][4];
+__device__ long long g_k2_misc[16][4];
+#define K2_TR(slot) do { if (blockIdx.x == 37 && blockIdx.y == 1 && lane == 0 && it == 2) g_k2_trace[warp][kc][slot] = clock64(); } while (0)
+#define K2_TM(slot) do { if (blockIdx.x == 37 && blockIdx.y == 1 && lane == 0 && it == 2) g_k2_misc[warp][slot] = clock64(); } while (0)
+#else
+#define K2_TR(slot) do {} while (0)
+#define K2_TM(slot) do {} while (0)
+#endif
+
 template <bool WRITE_GRAD, bool BTV, int TY>
 __global__ void __launch_bounds__(K2Fill<TY>::threads, K2Fill<TY>::ctas)
 k_gradient_update(const __grid_constant__ CUtensorMap rmap, const float* __restrict__ x_cur, float* __restrict__ x_next,
@@ -398,6 +431,7 @@ k_gradient_update(const __grid_constant__ CUtensorMap rmap, const float* __restr
     const int tx0 = (blockIdx.x % ntx) * K2_T, ty0 = (blockIdx.x / ntx) * TY;
     const InvXf* invb = inv + (size_t)b * N;
     const int nk = P.n_kept;
+    K2_TM(0);
     if (tid == 0) {
 #pragma unroll
         for (int i = 0; i < K2_STAGES; ++i) mbar_init(&stage_bar[i], 3);   // three async copies per stage
@@ -410,6 +444,84 @@ k_gradient_update(const __grid_constant__ CUtensorMap rmap, const float* __restr
         const int row = i / (K2_US / 4), c4 = i - row * (K2_US / 4);
         reinterpret_cast<float4*>(ut + (4 * row + 3) * K2_US)[c4] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);   // rows of buffer 1 follow buffer 0
     }
+
+    // The roles part here and never meet again except at the chunk barriers (bar 0, every thread, twice per chunk), so that each
+    // side can be compiled and run with its own register budget.
+    if (!gather_role) {
+        if (TY == 64 && K2_REG_SPLIT) asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+        for (int k0 = 0; k0 < nk; k0 += K2_CHUNK) {
+            const int nc = min(K2_CHUNK, nk - k0);
+            __syncthreads();   // the previous chunk's boxes are no longer read
+            __syncthreads();   // this chunk's boxes and transforms are in place (written by the gather warps)
+            // =================== fill warps ===================
+            // Warp fw owns the cell rows fw, fw+4, ... of the box and lane l the cell column l (boxes are at most 24
+            // cells wide).  Everything the fill reads was staged by async copies issued two copies earlier by one
+            // thread: no address arithmetic, bounds tests or table building is left in these warps.
+            const int fw = warp - K2_GW;
+            constexpr int ROWS = (K2_UR / 4 + K2_FW - 1) / K2_FW;   // cell rows per fill warp
+            const size_t slot0 = (size_t)(b_base + b) * N + k0;
+            const int ncw = w + 2 * K2_TPAD, nrw = h + 2 * K2_TPAD;
+            auto stage_copy = [&](int kq) {   // one thread: residual box + tap rows of copy kq -> stage (k0+kq) % 4
+                const KBox bq = boxes[kq];
+                K2Stage* S = stages + ((k0 + kq) & (K2_STAGES - 1));
+                unsigned long long* bar = &stage_bar[(k0 + kq) & (K2_STAGES - 1)];
+                tma_load_3d(&S->r[0][0], &rmap, bq.cbx0 & ~3, bq.cby0, (int)(slot0 + kq), bar, K2_RBOX_BYTES);
+                bulk_load(&S->ctap[0][0], tapc + ((slot0 + kq) * ncw + bq.cbx0 + K2_TPAD) * 4, K2_TAP_BYTES, bar);
+                bulk_load(&S->rtap[0][0], tapr + ((slot0 + kq) * nrw + bq.cby0 + K2_TPAD) * 4, K2_TAP_BYTES, bar);
+            };
+            const bool issuer = (fw == 0 && lane == 0);
+            int next_q = 0;   // issuer only: first copy of the chunk whose staging has not been issued yet
+            if (issuer) for (; next_q < K2_AHEAD && next_q < nc; ++next_q) stage_copy(next_q);
+            for (int kc = 0; kc < nc; ++kc) {
+                const int ub = kc & 1, gk = k0 + kc;
+                const KBox bc = boxes[kc];
+                const bool live = !(bc.ncxy >> 16);
+                const int ncx = bc.ncxy & 0xff, ncy = (bc.ncxy >> 8) & 0xff;
+                K2_TR(0);
+                if (kc >= 2) { if (ub) bar_sync(BAR_EMPTY + 1, K2_THREADS); else bar_sync(BAR_EMPTY, K2_THREADS); }   // the gather of copy kc-2 has left this buffer
+                // Keep the staging K2_AHEAD copies ahead.  Copy q reuses the stage of copy q-4, which is free once every fill warp
+                // has finished q-4: true when q-4 < 0 (the chunk's first use; the previous chunk ended with __syncthreads) or
+                // when the barrier above was passed (kc >= 2: every fill warp arrived for kc, i.e. is done with kc-1 >= q-4).
+                K2_TR(1);
+                if (issuer)
+                    while (next_q <= kc + K2_AHEAD && next_q < nc && (next_q < K2_STAGES || (kc >= 2 && next_q - K2_STAGES <= kc - 1)))
+                        stage_copy(next_q++);
+                mbar_wait(&stage_bar[gk & (K2_STAGES - 1)], (gk / K2_STAGES) & 1);
+                K2_TR(2);
+                if (live && lane < ncx) {
+                    const K2Stage* S = stages + (gk & (K2_STAGES - 1));
+                    const float4 ca = S->ctap[lane][0], cb = S->ctap[lane][1];     // (wa0,wb0,wa1,wb1) (wa2,wb2,wa3,wb3)
+                    const int xo = (bc.cbx0 & 3) + lane;
+                    float4* ucol = reinterpret_cast<float4*>(ut + ub * (K2_US * K2_UR)) + lane;
+    #pragma unroll
+                    for (int j = 0; j < ROWS; ++j) {
+                        const int cyi = fw + K2_FW * j;
+                        if (cyi < ncy) {
+                            const float g = fmul(0.25f, fmul(P.two_ldf, S->r[cyi][xo]));   // g_hr on the cell's 2x2 positions
+                            const float t0 = fmul(ca.y, g);                           // phase 0: taps (0, g)
+                            const float t1 = fadd(fmul(ca.z, g), fmul(ca.w, g));      // phase 1: taps (g, g)
+                            const float t2 = fmul(cb.x, g);                           // phase 2: taps (g, 0); phase 3: (0, 0)
+                            const float4 ra = S->rtap[cyi][0], rc = S->rtap[cyi][1];
+                            float4* dst = ucol + cyi * K2_US;                         // row 4*cyi
+                            dst[0] = make_float4(fmul(ra.y, t0), fmul(ra.y, t1), fmul(ra.y, t2), 0.0f);
+                            dst[K2_US / 4] = make_float4(fadd(fmul(ra.z, t0), fmul(ra.w, t0)), fadd(fmul(ra.z, t1), fmul(ra.w, t1)),
+                                                         fadd(fmul(ra.z, t2), fmul(ra.w, t2)), 0.0f);
+                            dst[2 * (K2_US / 4)] = make_float4(fmul(rc.x, t0), fmul(rc.x, t1), fmul(rc.x, t2), 0.0f);
+                        }
+                    }
+                }
+                if (live && tid - K2_NG < TY) {   // row products of the rotate coordinates for the gather warps
+                    const float Yf = (float)(ty0 + tid - K2_NG);
+                    rowp[ub * TY + tid - K2_NG] = make_float2(fmul(xfs[kc].b1, Yf), fmul(xfs[kc].b4, Yf));
+                }
+                __syncwarp();
+                K2_TR(3);
+                if (lane == 0) mbar_arrive(&full_bar[ub]);
+            }
+        }
+        return;
+    }
+    if (TY == 64 && K2_REG_SPLIT) asm volatile("setmaxnreg.inc.sync.aligned.u32 88;");
 
     // the two pixels of a row (columns lane, lane+32) travel as the two lanes of packed fp32 registers
     const float X0f = (float)(tx0 + lane), X1f = (float)(tx0 + lane + 32);
@@ -454,103 +566,48 @@ k_gradient_update(const __grid_constant__ CUtensorMap rmap, const float* __restr
         }
         __syncthreads();
 
-        if (gather_role) {
-            // =================== gather warps ===================
-            for (int kc = 0; kc < nc; ++kc) {
-                mbar_wait(&full_bar[kc & 1], ((k0 + kc) >> 1) & 1);   // u tile of copy kc is complete (no rendezvous among the gather warps)
-                const KBox bx = boxes[kc];
-                if (!(bx.ncxy >> 16)) {
-                    const InvXf T = xfs[kc];
-                    // byte address of tap (y0,x0) = 4*(y0*US + x0) + cst: box origin, buffer and tile address folded into cst
-                    int cst = 4 * (bx.cst + (kc & 1) * (K2_US * K2_UR)) + (int)smem_u32(ut);
-                    asm volatile("" : "+r"(cst));   // opaque and ordered after the wait above: no tap load can be hoisted over it
-                    const float cstf = denorm_int(cst);
-                    const f32x2 cstd = pk(cstf, cstf);
-                    const f32x2 b2p = pk(T.b2, T.b2), b5p = pk(T.b5, T.b5);
-                    // products stay scalar (a packed product feeding a packed sum would be contracted, asr_common.cuh)
-                    const f32x2 axp = pk(fmul(T.b0, X0f), fmul(T.b0, X1f)), ayp = pk(fmul(T.b3, X0f), fmul(T.b3, X1f));
+        // =================== gather warps ===================
+        K2_TM(1);
+        for (int kc = 0; kc < nc; ++kc) {
+            K2_TR(0);
+            mbar_wait(&full_bar[kc & 1], ((k0 + kc) >> 1) & 1);   // u tile of copy kc is complete (no rendezvous among the gather warps)
+            K2_TR(1);
+            const KBox bx = boxes[kc];
+            if (!(bx.ncxy >> 16)) {
+                const InvXf T = xfs[kc];
+                // byte address of tap (y0,x0) = 4*(y0*US + x0) + cst: box origin, buffer and tile address folded into cst
+                int cst = 4 * (bx.cst + (kc & 1) * (K2_US * K2_UR)) + (int)smem_u32(ut);
+                asm volatile("" : "+r"(cst));   // opaque and ordered after the wait above: no tap load can be hoisted over it
+                const float cstf = denorm_int(cst);
+                const f32x2 cstd = pk(cstf, cstf);
+                const f32x2 b2p = pk(T.b2, T.b2), b5p = pk(T.b5, T.b5);
+                // products stay scalar (a packed product feeding a packed sum would be contracted, asr_common.cuh)
+                const f32x2 axp = pk(fmul(T.b0, X0f), fmul(T.b0, X1f)), ayp = pk(fmul(T.b3, X0f), fmul(T.b3, X1f));
 #pragma unroll
-                    for (int r = 0; r < K2_ROWS; ++r) {
-                        const float2 rp = rowp[(kc & 1) * TY + warp + K2_GW * r];   // row products, built by the fill warps
-                        const float bxr = rp.x, byr = rp.y;
-                        const f32x2 ix = add2(add2(axp, pk(bxr, bxr)), b2p);
-                        const f32x2 iy = add2(add2(ayp, pk(byr, byr)), b5p);
-                        // floor on both lanes: fl_rd(v + 1.5*2^23) - 1.5*2^23
-                        const f32x2 fxf = sub2(add2_rd(ix, magic2), magic2), fyf = sub2(add2_rd(iy, magic2), magic2);
-                        // (x_ceil - x) == 1 - (x - x_floor) bit for bit unless x in (-1,0), where that weight only
-                        // multiplies the tap x_floor = -1, which lies outside the canvas and is an exact zero of u
-                        const f32x2 wx1 = sub2(ix, fxf), wx0 = sub2(one2, wx1);
-                        const f32x2 wy1 = sub2(iy, fyf), wy0 = sub2(one2, wy1);
-                        const f32x2 tp = tap_addr2<K2_US>(fxf, fyf, cstd);
-                        const unsigned ta = (unsigned)tp, tb = (unsigned)(tp >> 32);
-                        accp[r] = add2(accp[r], bilerp2(pk(lds_tap<0>(ta), lds_tap<0>(tb)), pk(lds_tap<4>(ta), lds_tap<4>(tb)),
-                                                        pk(lds_tap<4 * K2_US>(ta), lds_tap<4 * K2_US>(tb)),
-                                                        pk(lds_tap<4 * K2_US + 4>(ta), lds_tap<4 * K2_US + 4>(tb)), wx0, wx1, wy0, wy1));
-                    }
+                for (int r = 0; r < K2_ROWS; ++r) {
+                    const float2 rp = rowp[(kc & 1) * TY + warp + K2_GW * r];   // row products, built by the fill warps
+                    const float bxr = rp.x, byr = rp.y;
+                    const f32x2 ix = add2(add2(axp, pk(bxr, bxr)), b2p);
+                    const f32x2 iy = add2(add2(ayp, pk(byr, byr)), b5p);
+                    // floor on both lanes: fl_rd(v + 1.5*2^23) - 1.5*2^23
+                    const f32x2 fxf = sub2(add2_rd(ix, magic2), magic2), fyf = sub2(add2_rd(iy, magic2), magic2);
+                    // (x_ceil - x) == 1 - (x - x_floor) bit for bit unless x in (-1,0), where that weight only
+                    // multiplies the tap x_floor = -1, which lies outside the canvas and is an exact zero of u
+                    const f32x2 wx1 = sub2(ix, fxf), wx0 = sub2(one2, wx1);
+                    const f32x2 wy1 = sub2(iy, fyf), wy0 = sub2(one2, wy1);
+                    const f32x2 tp = tap_addr2<K2_US>(fxf, fyf, cstd);
+                    const unsigned ta = (unsigned)tp, tb = (unsigned)(tp >> 32);
+                    accp[r] = add2(accp[r], bilerp2(pk(lds_tap<0>(ta), lds_tap<0>(tb)), pk(lds_tap<4>(ta), lds_tap<4>(tb)),
+                                                    pk(lds_tap<4 * K2_US>(ta), lds_tap<4 * K2_US>(tb)),
+                                                    pk(lds_tap<4 * K2_US + 4>(ta), lds_tap<4 * K2_US + 4>(tb)), wx0, wx1, wy0, wy1));
                 }
-                // hand the buffer back; the last two hand-backs of a chunk have no taker
-                if (kc + 2 < nc) { if (kc & 1) bar_arrive(BAR_EMPTY + 1, K2_THREADS); else bar_arrive(BAR_EMPTY, K2_THREADS); }
             }
-        } else {
-            // =================== fill warps ===================
-            // Warp fw owns the cell rows fw, fw+4, ... of the box and lane l the cell column l (boxes are at most 24
-            // cells wide).  Everything the fill reads was staged by async copies issued two copies earlier by one
-            // thread: no address arithmetic, bounds tests or table building is left in these warps.
-            const int fw = warp - K2_GW;
-            constexpr int ROWS = (K2_UR / 4 + K2_FW - 1) / K2_FW;   // cell rows per fill warp
-            const size_t slot0 = (size_t)(b_base + b) * N + k0;
-            const int ncw = w + 2 * K2_TPAD, nrw = h + 2 * K2_TPAD;
-            auto stage_copy = [&](int kq) {   // one thread: residual box + tap rows of copy kq -> stage (k0+kq) % 4
-                const KBox bq = boxes[kq];
-                K2Stage* S = stages + ((k0 + kq) & (K2_STAGES - 1));
-                unsigned long long* bar = &stage_bar[(k0 + kq) & (K2_STAGES - 1)];
-                tma_load_3d(&S->r[0][0], &rmap, bq.cbx0 & ~3, bq.cby0, (int)(slot0 + kq), bar, K2_RBOX_BYTES);
-                bulk_load(&S->ctap[0][0], tapc + ((slot0 + kq) * ncw + bq.cbx0 + K2_TPAD) * 4, K2_TAP_BYTES, bar);
-                bulk_load(&S->rtap[0][0], tapr + ((slot0 + kq) * nrw + bq.cby0 + K2_TPAD) * 4, K2_TAP_BYTES, bar);
-            };
-            const bool issuer = (fw == 0 && lane == 0);
-            if (issuer) { stage_copy(0); if (nc > 1) stage_copy(1); }
-            for (int kc = 0; kc < nc; ++kc) {
-                const int ub = kc & 1, gk = k0 + kc;
-                const KBox bc = boxes[kc];
-                const bool live = !(bc.ncxy >> 16);
-                const int ncx = bc.ncxy & 0xff, ncy = (bc.ncxy >> 8) & 0xff;
-                if (kc >= 2) { if (ub) bar_sync(BAR_EMPTY + 1, K2_THREADS); else bar_sync(BAR_EMPTY, K2_THREADS); }   // the gather of copy kc-2 has left this buffer
-                // every fill warp is past copy kc-2 here, so the stage of copy kc+2 (the same one) is free
-                if (issuer && kc + 2 < nc) stage_copy(kc + 2);
-                mbar_wait(&stage_bar[gk & (K2_STAGES - 1)], (gk / K2_STAGES) & 1);
-                if (live && lane < ncx) {
-                    const K2Stage* S = stages + (gk & (K2_STAGES - 1));
-                    const float4 ca = S->ctap[lane][0], cb = S->ctap[lane][1];     // (wa0,wb0,wa1,wb1) (wa2,wb2,wa3,wb3)
-                    const int xo = (bc.cbx0 & 3) + lane;
-                    float4* ucol = reinterpret_cast<float4*>(ut + ub * (K2_US * K2_UR)) + lane;
-#pragma unroll
-                    for (int j = 0; j < ROWS; ++j) {
-                        const int cyi = fw + K2_FW * j;
-                        if (cyi < ncy) {
-                            const float g = fmul(0.25f, fmul(P.two_ldf, S->r[cyi][xo]));   // g_hr on the cell's 2x2 positions
-                            const float t0 = fmul(ca.y, g);                           // phase 0: taps (0, g)
-                            const float t1 = fadd(fmul(ca.z, g), fmul(ca.w, g));      // phase 1: taps (g, g)
-                            const float t2 = fmul(cb.x, g);                           // phase 2: taps (g, 0); phase 3: (0, 0)
-                            const float4 ra = S->rtap[cyi][0], rc = S->rtap[cyi][1];
-                            float4* dst = ucol + cyi * K2_US;                         // row 4*cyi
-                            dst[0] = make_float4(fmul(ra.y, t0), fmul(ra.y, t1), fmul(ra.y, t2), 0.0f);
-                            dst[K2_US / 4] = make_float4(fadd(fmul(ra.z, t0), fmul(ra.w, t0)), fadd(fmul(ra.z, t1), fmul(ra.w, t1)),
-                                                         fadd(fmul(ra.z, t2), fmul(ra.w, t2)), 0.0f);
-                            dst[2 * (K2_US / 4)] = make_float4(fmul(rc.x, t0), fmul(rc.x, t1), fmul(rc.x, t2), 0.0f);
-                        }
-                    }
-                }
-                if (live && tid - K2_NG < TY) {   // row products of the rotate coordinates for the gather warps
-                    const float Yf = (float)(ty0 + tid - K2_NG);
-                    rowp[ub * TY + tid - K2_NG] = make_float2(fmul(xfs[kc].b1, Yf), fmul(xfs[kc].b4, Yf));
-                }
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&full_bar[ub]);
-            }
+            K2_TR(2);
+            // hand the buffer back; the last two hand-backs of a chunk have no taker
+            if (kc + 2 < nc) { if (kc & 1) bar_arrive(BAR_EMPTY + 1, K2_THREADS); else bar_arrive(BAR_EMPTY, K2_THREADS); }
         }
     }
-    if (!gather_role) return;
+    K2_TM(2);
 
     // ---- epilogue: TV (tf.image.image_gradients), L2, L1, optimizer ---------------
     // Two rows (four pixels) at a time: every global load of the batch -- x, its four neighbours and the
@@ -662,6 +719,7 @@ k_gradient_update(const __grid_constant__ CUtensorMap rmap, const float* __restr
             }
         }
     }
+    K2_TM(3);
 }
 
 // ================================================================================================
@@ -953,8 +1011,10 @@ static unsigned div_magic(int d) { return (unsigned)((0x100000000ull + (unsigned
 static int configure_kernels() {
     static unsigned long long done = 0;   // one bit per device: the attribute belongs to the (function, device) pair
     if (!first_use_on_device(&done)) return ASR_OK;
-    ASR_CUDA_TRY(cudaFuncSetAttribute(k_forward_residual<K1_XR_SMALL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k1_smem<K1_XR_SMALL>()));
-    ASR_CUDA_TRY(cudaFuncSetAttribute(k_forward_residual<K1_XR_BIG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k1_smem<K1_XR_BIG>()));
+    ASR_CUDA_TRY(cudaFuncSetAttribute(k_forward_residual<K1_XR_SMALL, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k1_smem<K1_XR_SMALL>()));
+    ASR_CUDA_TRY(cudaFuncSetAttribute(k_forward_residual<K1_XR_BIG, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k1_smem<K1_XR_BIG>()));
+    ASR_CUDA_TRY(cudaFuncSetAttribute(k_forward_residual<K1_XR_SMALL, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k1_smem<K1_XR_SMALL>()));
+    ASR_CUDA_TRY(cudaFuncSetAttribute(k_forward_residual<K1_XR_BIG, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k1_smem<K1_XR_BIG>()));
 #define ASR_K2_ATTR(WG, BT, TY) \
     ASR_CUDA_TRY(cudaFuncSetAttribute(k_gradient_update<WG, BT, TY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k2_smem<TY>()));
 #define ASR_K2_ATTRS(TY) ASR_K2_ATTR(false, false, TY) ASR_K2_ATTR(false, true, TY) ASR_K2_ATTR(true, false, TY) ASR_K2_ATTR(true, true, TY)
@@ -975,6 +1035,15 @@ static int launch_loss(const Device& D, int n_params, float* d_loss, int B, int 
 }  // namespace asr
 
 using namespace asr;
+
+#ifdef ASR_K2_TRACE
+extern "C" int asr_debug_k2_trace(long long* h_trace, long long* h_misc) {
+    ASR_CUDA_TRY(cudaDeviceSynchronize());
+    ASR_CUDA_TRY(cudaMemcpyFromSymbol(h_trace, g_k2_trace, sizeof(long long) * 16 * 128 * 4));
+    ASR_CUDA_TRY(cudaMemcpyFromSymbol(h_misc, g_k2_misc, sizeof(long long) * 16 * 4));
+    return ASR_OK;
+}
+#endif
 
 extern "C" int asr_solve_workspace_bytes(int B, int N, int h, int w, int H, int W, int max_iter, size_t* bytes) {
     if (!bytes) return fail(ASR_ENULL, "bytes is NULL");
@@ -1007,10 +1076,21 @@ static int k2_tile_height(int n_images, int H, int W) {
         }                                                                                                             \
     } while (0)
 
-#define ASR_LAUNCH_K1(small, t1, nk, nimg, st, ...)                                                                          \
-    do {                                                                                                                     \
-        if (small) ASR_LAUNCH_TIMED(0, k_forward_residual<K1_XR_SMALL>, dim3(t1, nk, nimg), dim3(K1_PC, K1_THREADS / K1_PC), k1_smem<K1_XR_SMALL>(), st, __VA_ARGS__); \
-        else ASR_LAUNCH_TIMED(0, k_forward_residual<K1_XR_BIG>, dim3(t1, nk, nimg), dim3(K1_PC, K1_THREADS / K1_PC), k1_smem<K1_XR_BIG>(), st, __VA_ARGS__);           \
+static bool k1_conflict_free() {   // ASR_K1_CF=0 selects the 48x4 thread map (experiments, tests)
+    const char* e = getenv("ASR_K1_CF");
+    return !(e && e[0] == '0');
+}
+#define ASR_LAUNCH_K1_V(XR, CF, bdim, t1, nk, nimg, st, ...) \
+    ASR_LAUNCH_TIMED(0, (k_forward_residual<XR, CF>), dim3(t1, nk, nimg), bdim, k1_smem<XR>(), st, __VA_ARGS__)
+#define ASR_LAUNCH_K1(small, t1, nk, nimg, st, ...)                                                                  \
+    do {                                                                                                             \
+        if (k1_conflict_free()) {                                                                                    \
+            if (small) ASR_LAUNCH_K1_V(K1_XR_SMALL, true, dim3(32, 6), t1, nk, nimg, st, __VA_ARGS__);               \
+            else ASR_LAUNCH_K1_V(K1_XR_BIG, true, dim3(32, 6), t1, nk, nimg, st, __VA_ARGS__);                       \
+        } else {                                                                                                     \
+            if (small) ASR_LAUNCH_K1_V(K1_XR_SMALL, false, dim3(48, 4), t1, nk, nimg, st, __VA_ARGS__);              \
+            else ASR_LAUNCH_K1_V(K1_XR_BIG, false, dim3(48, 4), t1, nk, nimg, st, __VA_ARGS__);                      \
+        }                                                                                                            \
     } while (0)
 
 static int solve_impl(const AsrSolveParams* params, int n_params, const float* d_copies, const float* h_angles,
