@@ -13,7 +13,12 @@ Images shard across ranks with no collective in the solve; the masks are gathere
   cpu_baseline  the CPU oracle (a port of the reference's TensorFlow arithmetic) on this box's host cores
 
 `--impl reference` times that CPU port alone (the reference itself is TensorFlow 2.7 code that cannot be
-installed here: DESIGN.md), on a bounded sample of the same workload.
+installed here: DESIGN.md, profiles/r02_tf_install_attempt.log), on a bounded sample of the same workload: the
+first step is always one FULL 300-iteration solve of one image; later steps shorten the iteration count only if
+the requested --steps would not fit the time budget.
+
+`--scaling strong` runs BASELINE configs[1] as written: `--images` images IN TOTAL (default 500) sharded over the
+ranks in contiguous blocks (sharding.shard_bounds); the default is weak scaling (`--images` per GPU).
 """
 import argparse
 import json
@@ -51,9 +56,12 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--images", type=int, default=500, help="images per GPU per step (weak scaling)")
     ap.add_argument("--images-in-flight", type=int, default=0, help="images per kernel-launch group (0 = all)")
-    ap.add_argument("--cpu-seconds", type=float, default=15.0, help="budget of the cpu_baseline sample")
-    ap.add_argument("--ref-iters", type=int, default=6, help="--impl reference: solver iterations per step (sample)")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"], help="weak: --images per GPU; strong: --images in total")
+    ap.add_argument("--cpu-seconds", type=float, default=45.0, help="budget of the cpu_baseline sample (one full solve when it fits)")
+    ap.add_argument("--ref-seconds", type=float, default=240.0, help="--impl reference: wall-clock budget of the whole run")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-l2-probe", action="store_true", help="skip the L2 bandwidth microbenchmark and the L2-resident run")
+    ap.add_argument("--l2-images", type=int, default=4, help="images in flight of the L2-resident run (about 20 MB of working set each)")
     return ap.parse_args()
 
 
@@ -121,11 +129,12 @@ def oracle_sample(copies_np, ang, sh, iters):
 def cpu_baseline(copies_np, ang, sh, budget_s):
     dt3, cores = oracle_sample(copies_np, ang, sh, 3)
     per_iter = dt3 / 3
-    n = int(max(5, min(150, budget_s / per_iter)))
+    n = ITERS if per_iter * ITERS <= budget_s else int(max(5, budget_s / per_iter))
     dt, cores = oracle_sample(copies_np, ang, sh, n)
     per_iter = dt / n
+    how = "one full solve" if n == ITERS else "extrapolated linearly in iterations"
     return {"value": 1.0 / (per_iter * ITERS), "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": f"1 image x {NUM_AUG} copies x {n} of {ITERS} iterations in {dt:.1f} s, extrapolated linearly in iterations"}
+            "sample": f"1 image x {NUM_AUG} copies x {n} of {ITERS} iterations in {dt:.1f} s ({how})"}
 
 
 def run_reference(args, rank, world):
@@ -134,22 +143,33 @@ def run_reference(args, rank, world):
     from deeplabv3plus_augmented_superresolution_b200.synthetic import make_augmented_copies
     copies, ang, sh = make_augmented_copies(1, NUM_AUG, LR_HW, HR_HW, 0.15, 80, seed=1234, value=1.0)
     c = copies[0].numpy()
-    times = []
-    cores = 1
-    for s in range(args.warmup + args.steps):
-        dt, cores = oracle_sample(c, ang[0], sh[0], args.ref_iters)
-        if s >= args.warmup:
+    n_steps = args.warmup + args.steps
+    # step 0 (a warm-up unless --warmup 0) is ONE FULL solve whenever half the budget can pay for it; it also calibrates what
+    # the remaining steps can afford
+    t3, cores = oracle_sample(c, ang[0], sh[0], 3)
+    full = (t3 / 3) * ITERS <= 0.5 * args.ref_seconds
+    t_full, cores = oracle_sample(c, ang[0], sh[0], ITERS) if full else ((t3 / 3) * ITERS, cores)
+    left = max(1, n_steps - 1)
+    iters = ITERS if t_full * left <= max(0.0, args.ref_seconds - t_full) else int(max(6, ITERS * (args.ref_seconds - t_full) / (t_full * left)))
+    iters = min(ITERS, max(6, iters))
+    times = [t_full * iters / ITERS] if args.warmup == 0 else []      # per-step times, normalised to `iters` iterations
+    for s_ in range(1, n_steps):
+        dt, cores = oracle_sample(c, ang[0], sh[0], iters)
+        if s_ >= args.warmup:
             times.append(dt)
-    per_iter = sum(times) / (len(times) * args.ref_iters)
+    per_iter = sum(times) / (len(times) * iters)
     value = 1.0 / (per_iter * ITERS)
-    sample = f"each step = 1 image x {NUM_AUG} copies x {args.ref_iters} of {ITERS} iterations; images/s extrapolated linearly in iterations"
+    sample = ((f"step 0 = 1 image x {NUM_AUG} copies x {ITERS} of {ITERS} iterations (one full solve, {t_full:.1f} s = {1.0 / t_full:.5f} images/s); " if full else
+               f"a full solve would take ~{t_full:.0f} s on this host (3-iteration probe), more than half of --ref-seconds, so none was run; ")
+              f"timed steps = 1 image x {iters} of {ITERS} iterations each" + ("" if iters == ITERS else ", images/s extrapolated linearly in iterations"))
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": 1e3 * sum(times) / len(times), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": 1e3 * sum(times) / len(times), "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
             "dtype": "f32", "data": "synthetic", "impl": "reference",
             "config": {"workload": "configs[1] SR_single_class batch shape: 100 copies, 128^2->512^2, 300 Adam+AMSGrad iterations",
                        "note": "CPU port (oracle/asr_oracle.c) of the reference's TensorFlow op sequence on all host cores; the reference "
-                               "itself needs tensorflow==2.7.0 + tensorflow-addons==0.15.0, which cannot be installed here", "sample": sample},
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+                               "itself needs tensorflow==2.7.0 + tensorflow-addons==0.15.0, which cannot be installed here "
+                               "(profiles/r02_tf_install_attempt.log)", "sample": sample},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample, "full_solve_s": t_full if full else None},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     emit(line)
@@ -191,9 +211,16 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     L = A.lib()
 
-    B = args.images
-    n_total = B * world
-    # synthetic stand-in for the hdf5 augmented-copies files: rank r holds images [r*B, (r+1)*B)
+    if args.scaling == "strong":
+        n_total = args.images                                   # configs[1] as written: 500 images over all GPUs
+        lo, hi = sharding.shard_bounds(n_total, world, rank)
+    else:
+        n_total = args.images * world                            # the same per-GPU batch on every rank
+        lo, hi = rank * args.images, (rank + 1) * args.images
+    B = hi - lo
+    if B <= 0:
+        raise SystemExit(f"rank {rank} has no images: --images {args.images} over {world} ranks")
+    # synthetic stand-in for the hdf5 augmented-copies files: rank r holds images [lo, hi) of the run
     copies, ang, sh = make_augmented_copies(B, NUM_AUG, LR_HW, HR_HW, 0.15, 80, seed=1234 + 7 * rank, value=1.0, device=dev)
 
     def make_solver():
@@ -204,13 +231,17 @@ def main():
     ws_th = torch.empty(2 * B, dtype=torch.float32, device=dev)
     masks = torch.empty((B, HR_HW[0], HR_HW[1]), dtype=torch.int32, device=dev)
 
-    def hot_path(dev_copies):
+    def hot_path(dev_copies, in_flight=None, n=None):
+        n = B if n is None else n
         sr = make_solver()
-        sr.optimizer.iterations = ITERS * B * rank          # one optimizer shared by the whole (sharded) run
-        plist = [sr._solve_params(sr.optimizer.iterations + j * ITERS, images_in_flight=args.images_in_flight) for j in range(B)]
-        x = sr.augmented_superresolution_batched(dev_copies, ang, sh, params_list=plist)
-        A.check(L.asr_threshold(x.data_ptr(), B, HR_HW[0] * HR_HW[1], 8, 0.65, None, masks.data_ptr(), ws_th.data_ptr(),
+        sr.optimizer.iterations = ITERS * lo                     # one optimizer shared by the whole (sharded) run
+        fl = args.images_in_flight if in_flight is None else in_flight
+        plist = [sr._solve_params(sr.optimizer.iterations + j * ITERS, images_in_flight=fl) for j in range(n)]
+        x = sr.augmented_superresolution_batched(dev_copies[:n], ang[:n], sh[:n], params_list=plist)
+        A.check(L.asr_threshold(x.data_ptr(), n, HR_HW[0] * HR_HW[1], 8, 0.65, None, masks.data_ptr(), ws_th.data_ptr(),
                                 C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+        if n != B:
+            return masks[:n]
         return sharding.gather_masks(masks.to(torch.uint8), n_total) if world > 1 else masks
 
     def barrier():
@@ -258,20 +289,47 @@ def main():
 
     e2e_step()
     ms_e2e = timed(e2e_step, args.steps)
-    e2e = {"value": n_total * args.steps / (ms_e2e / 1e3), "unit": UNIT,
-           "h2d_bytes_per_step": int(host_copies.numel() * 4 * world), "d2h_bytes_per_step": int(host_masks.numel() * 4 * world)}
-
-    lt = torch.tensor([launches], dtype=torch.int64, device=dev)
+    bytes_io = torch.tensor([host_copies.numel() * 4, host_masks.numel() * 4, launches], dtype=torch.int64, device=dev)
     if world > 1:
-        dist.all_reduce(lt)
+        dist.all_reduce(bytes_io)
+    e2e = {"value": n_total * args.steps / (ms_e2e / 1e3), "unit": UNIT,
+           "h2d_bytes_per_step": int(bytes_io[0].item()), "d2h_bytes_per_step": int(bytes_io[1].item()),
+           "api": "Superresolution.augmented_superresolution_batched (the batched extension of the reference-named class; the reference's own "
+                  "per-image signature is measured in profiles/ as config 1) + asr_threshold, pinned host buffers in and out"}
+
+    # ---- L2 regime (rank 0, one GPU): measured L2 read bandwidth, and the solve with so few images in flight that
+    #      their whole working set (copies + residuals + x + slots + tap tables, ~20 MB per image) stays in the 126 MB L2
+    l2 = None
+    if rank == 0 and world == 1 and not args.no_l2_probe:
+        nb = 64 << 20
+        buf = torch.empty(nb, dtype=torch.uint8, device=dev).fill_(1)
+        sink = torch.zeros(1, dtype=torch.int32, device=dev)
+        st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        A.check(L.asr_l2_read_probe(buf.data_ptr(), nb, 2, sink.data_ptr(), st))            # warm
+        best = 0.0
+        for _ in range(3):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            passes = 40
+            e0.record(); A.check(L.asr_l2_read_probe(buf.data_ptr(), nb, passes, sink.data_ptr(), st)); e1.record()
+            torch.cuda.synchronize()
+            best = max(best, nb * passes / (e0.elapsed_time(e1) / 1e3) / 1e9)
+        del buf
+        n_l2 = min(B, 8 * args.l2_images)
+        hot_path(copies, in_flight=args.l2_images, n=n_l2)
+        ms_l2 = timed(lambda: hot_path(copies, in_flight=args.l2_images, n=n_l2), 1)
+        ips = n_l2 / (ms_l2 / 1e3)
+        ach = ips * ITERS * BYTES_PER_IMAGE_ITER / 1e9
+        l2 = {"peak": best, "unit": "GB/s", "peak_source": "asr_l2_read_probe: 64 MB buffer read 40x with ld.global.cg, best of 3, CUDA events",
+              "resident_run": {"images_in_flight": args.l2_images, "images": n_l2, "value": ips, "unit": UNIT, "achieved": ach, "frac": ach / best,
+                               "note": "algorithmic bytes of SURVEY 8(d) / time with the working set of the launch group L2-resident; "
+                                       "ncu lts__throughput of the two kernels: profiles/r02_ncu_solve_kernels.txt"}}
 
     if rank == 0:
         peaks, peak_kind = load_peaks()
         dom = 1 if kms[1] >= kms[0] else 0
         names = ["k_forward_residual", "k_gradient_update"]
-        per_launch_images = B if args.images_in_flight <= 0 else min(B, args.images_in_flight)
         avg_launch_s = (kms[dom] / max(1, kcnt[dom])) / 1e3
-        # launches of a short tail group carry fewer images: use the true mean images per launch
+        # launches of a short tail group carry fewer images: use the true mean images per launch (rank 0's share)
         images_per_launch = B * ITERS * args.steps / max(1, kcnt[dom])
         achieved = images_per_launch * BYTES_PER_IMAGE_ITER / avg_launch_s / 1e9
         traffic = None
@@ -281,30 +339,37 @@ def main():
         except Exception:
             pass
         iter_s = (kms[0] + kms[1]) / 1e3 / max(1, kcnt[1])
-        roofline = {"bound": "hbm", "kernel": names[dom], "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                    "frac": achieved / peaks["hbm_gbs"], "traffic": traffic, "peak_source": f"{peak_kind} (MEASURED_PEAKS.json hbm_gbs)",
-                    "share_of_step": kms[dom] / ms, "avg_launch_ms": avg_launch_s * 1e3,
-                    "forward_ms_total": kms[0], "update_ms_total": kms[1],
-                    "iteration_pair": {"achieved": images_per_launch * BYTES_PER_IMAGE_ITER / iter_s / 1e9,
-                                       "frac": images_per_launch * BYTES_PER_IMAGE_ITER / iter_s / 1e9 / peaks["hbm_gbs"]},
-                    "note": "the solve is FP32-issue bound, not bandwidth bound: see DESIGN.md 'Roofline' and profiles/"}
+        pair_gbs = images_per_launch * BYTES_PER_IMAGE_ITER / iter_s / 1e9
         # the bound that actually binds: fp32 lane-operations per second against 148 SMs x 128 lanes x the SM clock under load
         clk_hz = 1e6 * float((clocks or {}).get("sm_mhz") or peaks.get("sm_max_mhz") or 1965.0)
         fp_peak = N_SM * FP32_LANES_PER_SM * clk_hz
         fp_ach = images_per_launch * FP32_OPS_PER_IMAGE_ITER / iter_s
-        roofline["fp32_pipe"] = {"achieved": fp_ach / 1e12, "peak": fp_peak / 1e12, "unit": "T fp32 lane-op/s", "frac": fp_ach / fp_peak,
-                                 "ops_per_image_iteration": FP32_OPS_PER_IMAGE_ITER,
-                                 "note": "un-fused IEEE ops of the literal operator sequence (no FMA by contract); K1+K2 launch pair"}
+        roofline = {"bound": "hbm", "kernel": names[dom], "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                    "frac": achieved / peaks["hbm_gbs"], "frac_is": f"{names[dom]} alone (the dominant kernel); the whole iteration is pair_frac",
+                    "traffic": traffic, "peak_source": f"{peak_kind} (MEASURED_PEAKS.json hbm_gbs)",
+                    "share_of_step": kms[dom] / ms, "avg_launch_ms": avg_launch_s * 1e3,
+                    "forward_ms_total": kms[0], "update_ms_total": kms[1],
+                    "us_per_image_iteration": {"k_forward_residual": kms[0] * 1e3 / max(1, kcnt[0]) / images_per_launch,
+                                               "k_gradient_update": kms[1] * 1e3 / max(1, kcnt[1]) / images_per_launch},
+                    "pair_achieved": pair_gbs, "pair_frac": pair_gbs / peaks["hbm_gbs"],
+                    "fp32_pipe_frac": fp_ach / fp_peak,
+                    "fp32_pipe": {"achieved": fp_ach / 1e12, "peak": fp_peak / 1e12, "unit": "T fp32 lane-op/s", "frac": fp_ach / fp_peak,
+                                  "ops_per_image_iteration": FP32_OPS_PER_IMAGE_ITER,
+                                  "note": "un-fused IEEE ops of the literal operator sequence (no FMA by contract); K1+K2 launch pair"},
+                    "l2": l2,
+                    "note": "the solve is FP32-issue bound, not bandwidth bound (pair_frac is small by construction): DESIGN.md 'Roofline', profiles/"}
+        workload = (f"configs[1] SR_single_class batch: {args.images} images x 100 copies " +
+                    ("per GPU" if args.scaling == "weak" else f"in total, sharded over {world} GPU(s)") +
+                    ", 128^2->512^2, 300 Adam+AMSGrad iterations (test_SR.py hyper-parameters, shared-optimizer step offsets), threshold 0.65")
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-                "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+                "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f32",
                 "data": "synthetic",
-                "config": {"workload": "configs[1] SR_single_class batch: 500 images x 100 copies per GPU, 128^2->512^2, 300 Adam+AMSGrad "
-                                       "iterations (test_SR.py hyper-parameters, shared-optimizer step offsets), threshold 0.65",
-                           "images_per_gpu": B, "num_aug": NUM_AUG, "iterations": ITERS, "images_in_flight": args.images_in_flight,
+                "config": {"workload": workload, "images_total": n_total, "images_rank0": B, "num_aug": NUM_AUG, "iterations": ITERS,
+                           "images_in_flight": args.images_in_flight,
                            "parallelism": f"images sharded over {world} GPU(s), no collective in the solve, NCCL gather of masks",
-                           "l2": f"inputs are {copies.numel() * 4 / 1e9:.2f} GB per GPU (> 126 MB L2), no flush needed",
-                           "parity": "bit-identical to the CPU oracle (tests/test_parity_gpu.py)"},
-                "clocks": clocks, "e2e": e2e, "gpu_launches": int(lt.item()), "roofline": roofline}
+                           "l2": f"inputs are {copies.numel() * 4 / 1e9:.2f} GB on rank 0 (> 126 MB L2), no flush needed",
+                           "parity": "bit-identical to the CPU oracle (tests/test_parity_gpu.py); the oracle is a port, not TensorFlow (DESIGN.md 'Oracle')"},
+                "clocks": clocks, "e2e": e2e, "gpu_launches": int(bytes_io[2].item()), "roofline": roofline}
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(copies[0].cpu().numpy(), ang[0], sh[0], args.cpu_seconds)
         emit(line)

@@ -50,6 +50,7 @@ SIGNATURES = {
     "asr_kernel_launches": (C.c_longlong, []),
     "asr_profile_enable": (C.c_int, [C.c_int]),
     "asr_profile_read": (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_longlong)]),
+    "asr_l2_read_probe": (C.c_int, [C.c_void_p, C.c_size_t, C.c_int, C.c_void_p, C.c_void_p]),
     "asr_solve_workspace_bytes": (C.c_int, [C.c_int] * 7 + [C.POINTER(C.c_size_t)]),
     "asr_solve_batched": (C.c_int, [C.POINTER(AsrSolveParams), C.c_int, C.c_void_p, _fp, _fp, _u8p,
                                     C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,

@@ -572,9 +572,39 @@ __global__ void k_iou_counts(const int* __restrict__ yt, const int* __restrict__
     }
 }
 
+// ================================================================================================
+// measurement hook: L2 read bandwidth (bench.py's roofline.l2; SURVEY 8d asks for a measured L2 peak)
+// ================================================================================================
+// Every thread streams 16-byte words of a buffer that fits the L2 (ld.global.cg: L1 is bypassed), `passes` times over;
+// the first pass warms the L2, the caller times the launch with CUDA events and divides bytes * passes by it.
+__global__ void __launch_bounds__(256) k_l2_read(const uint4* __restrict__ buf, size_t n16, int passes, unsigned* __restrict__ sink) {
+    unsigned acc = 0;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (int p = 0; p < passes; ++p) {
+        size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+        for (; i + 3 * stride < n16; i += 4 * stride) {   // four independent loads in flight per thread
+            const uint4 a = __ldcg(buf + i), b = __ldcg(buf + i + stride), c = __ldcg(buf + i + 2 * stride), d = __ldcg(buf + i + 3 * stride);
+            acc ^= a.x ^ a.y ^ a.z ^ a.w ^ b.x ^ b.y ^ b.z ^ b.w ^ c.x ^ c.y ^ c.z ^ c.w ^ d.x ^ d.y ^ d.z ^ d.w;
+        }
+        for (; i < n16; i += stride) { const uint4 a = __ldcg(buf + i); acc ^= a.x ^ a.y ^ a.z ^ a.w; }
+    }
+    if (acc == 0x9e3779b9u) *sink = acc;   // keeps the loads alive; practically never true
+}
+
 }  // namespace asr
 
 using namespace asr;
+
+extern "C" int asr_l2_read_probe(const void* d_buf, size_t bytes, int passes, void* d_sink, void* stream) {
+    if (!d_buf || !d_sink) return fail(ASR_ENULL, "null argument");
+    if (bytes < 16 || passes <= 0 || !aligned16(d_buf)) return fail(ASR_EINVAL, "need bytes >= 16, passes > 0 and a 16-byte aligned buffer");
+    int dev = 0, n_sm = 148;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+    ASR_LAUNCH(k_l2_read, n_sm * 8, 256, 0, static_cast<cudaStream_t>(stream), static_cast<const uint4*>(d_buf), bytes / 16, passes,
+               static_cast<unsigned*>(d_sink));
+    ASR_CUDA_TRY(cudaGetLastError());
+    return ASR_OK;
+}
 
 extern "C" int asr_iou_counts(const int32_t* d_true, const int32_t* d_pred, int B, int64_t n, int class_id, int include_bg,
                               unsigned long long* d_counts, void* stream) {

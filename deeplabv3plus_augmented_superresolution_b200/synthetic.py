@@ -72,3 +72,47 @@ def make_augmented_copies(num_images: int, num_aug: int = 100, feature_size=(128
             m |= (ex * ex + ey * ey) <= 1.0
         out[b] = (m & inside_canvas).to(torch.float32) * value
     return out, angles, shifts
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# stand-ins for test_SR.py's inputs: an image with a ground-truth mask and an upstream "model"
+# ---------------------------------------------------------------------------------------------------------------
+def make_test_image(size=(512, 512), class_id: int = 8, seed: int = 5):
+    """An RGB image in [0,1] whose red channel marks a union of two ellipses, and its label image (values {0, class_id}).
+    Stands in for test_images/test_cat.jpg + test_cat_gt.png (there are no DeepLab weights here to segment a real cat)."""
+    H, W = size
+    rng = np.random.RandomState(seed)
+    yy, xx = np.mgrid[0:H, 0:W].astype(np.float64)
+    m = np.zeros((H, W), bool)
+    for _ in range(2):
+        cx, cy = rng.uniform(0.35 * W, 0.65 * W), rng.uniform(0.35 * H, 0.65 * H)
+        ra, rb, ph = rng.uniform(0.12 * W, 0.25 * W), rng.uniform(0.12 * H, 0.25 * H), rng.uniform(0, np.pi)
+        ux, uy = xx - cx, yy - cy
+        ex, ey = (np.cos(ph) * ux + np.sin(ph) * uy) / ra, (-np.sin(ph) * ux + np.cos(ph) * uy) / rb
+        m |= (ex * ex + ey * ey) <= 1.0
+    img = np.empty((H, W, 3), np.float32)
+    img[..., 0] = np.where(m, 0.9, 0.1)
+    img[..., 1] = 0.3 + 0.2 * rng.rand(H, W)
+    img[..., 2] = np.where(m, 0.2, 0.6)
+    return img, (m.astype(np.int32) * class_id)[..., None]
+
+
+class SyntheticSegmenter:
+    """The upstream producer interface of compute_augmented_feature_maps (`model.predict(images, batch_size) ->
+    [n, H/4, W/4, K] logits`, model.py in the reference, outside this repo).  Class `class_id` wins where the 4x4-pooled
+    red channel exceeds one half, background elsewhere; a fixed pseudo-random ripple keeps the other channels distinct."""
+
+    def __init__(self, classes: int = 21, class_id: int = 8, stride: int = 4):
+        self.classes, self.class_id, self.stride = classes, class_id, stride
+
+    def predict(self, images, batch_size=16):
+        x = images if isinstance(images, torch.Tensor) else torch.from_numpy(np.asarray(images, np.float32))
+        x = x.to(torch.float32)
+        n, H, W, _ = x.shape
+        s = self.stride
+        red = x[..., 0].reshape(n, H // s, s, W // s, s).mean(dim=(2, 4))
+        k = torch.arange(self.classes, device=x.device, dtype=torch.float32)
+        logits = 0.05 * torch.sin(k[None, None, None, :] * 1.7 + red[..., None] * 3.0)
+        logits[..., 0] += 2.0 * (0.5 - red)
+        logits[..., self.class_id] += 2.0 * (red - 0.5)
+        return logits.contiguous()

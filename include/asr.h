@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define ASR_VERSION 100
+#define ASR_VERSION 200
 
 enum {
     ASR_OK = 0,
@@ -81,6 +81,11 @@ const char* asr_last_error(void);
 long long asr_kernel_launches(void);
 int asr_profile_enable(int on);
 int asr_profile_read(double* ms2, long long* count2);
+
+/* Measurement hook (bench.py roofline.l2): one launch that reads `bytes` of d_buf `passes` times with L1 bypassed.
+ * With a buffer that fits the L2 and passes >> 1 the caller's CUDA-event time gives the L2 read bandwidth of the
+ * device the solve's L2-resident regime is compared against.  d_sink: 4 bytes.                                  */
+int asr_l2_read_probe(const void* d_buf, size_t bytes, int passes, void* d_sink, void* stream);
 
 /* ---- superresolution.py:102-137  Superresolution.augmented_superresolution ------------------
  * Solves B independent images in one call (SR_single_class.py:83-107 loops over them one by one).

@@ -10,7 +10,7 @@ int main(void) {
     size_t need = 0;
     AsrSolveParams p;
     memset(&p, 0, sizeof p);
-    if (asr_version() != 100) { printf("version %d\n", asr_version()); return 1; }
+    if (asr_version() != ASR_VERSION) { printf("version %d\n", asr_version()); return 1; }
     if (asr_solve_workspace_bytes(2, 100, 128, 128, 512, 512, 300, &need) != ASR_OK || need == 0) return 2;
     if (asr_solve_workspace_bytes(1, 4, 64, 64, 512, 512, 10, &need) != ASR_EUNSUPPORTED) return 3;
     if (strstr(asr_last_error(), "feature_size") == NULL) return 4;
