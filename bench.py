@@ -159,9 +159,14 @@ def run_reference(args, rank, world):
             times.append(dt)
     per_iter = sum(times) / (len(times) * iters)
     value = 1.0 / (per_iter * ITERS)
-    sample = ((f"step 0 = 1 image x {NUM_AUG} copies x {ITERS} of {ITERS} iterations (one full solve, {t_full:.1f} s = {1.0 / t_full:.5f} images/s); " if full else
-               f"a full solve would take ~{t_full:.0f} s on this host (3-iteration probe), more than half of --ref-seconds, so none was run; ")
-              f"timed steps = 1 image x {iters} of {ITERS} iterations each" + ("" if iters == ITERS else ", images/s extrapolated linearly in iterations"))
+    if full:
+        head = (f"step 0 = 1 image x {NUM_AUG} copies x {ITERS} of {ITERS} iterations (one full solve, {t_full:.1f} s = "
+                f"{1.0 / t_full:.5f} images/s); ")
+    else:
+        head = (f"a full solve would take ~{t_full:.0f} s on this host (3-iteration probe), more than half of --ref-seconds, "
+                f"so none was run; ")
+    sample = head + f"timed steps = 1 image x {iters} of {ITERS} iterations each" + \
+        ("" if iters == ITERS else ", images/s extrapolated linearly in iterations")
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * sum(times) / len(times), "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
             "dtype": "f32", "data": "synthetic", "impl": "reference",
