@@ -430,7 +430,7 @@ def test_same_process_second_device():
     from deeplabv3plus_augmented_superresolution_b200.synthetic import make_augmented_copies
     from deeplabv3plus_augmented_superresolution_b200.superresolution_scripts.superresolution import Superresolution
     P = A.SolveParams(num_iter=6)
-    sr = Superresolution(feature_size=(32, 32), output_size=(128, 128))
+    sr = Superresolution(1.0, 0.3, 0.7, 0.0, feature_size=(32, 32), output_size=(128, 128))
     outs = []
     for dev in ("cuda:0", "cuda:1", "cuda:0"):
         copies, ang, sh = make_augmented_copies(1, 5, (32, 32), (128, 128), 0.15, 20, seed=21, device=dev)
