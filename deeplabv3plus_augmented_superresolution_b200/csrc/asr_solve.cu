@@ -418,7 +418,6 @@ k_gradient_update(const __grid_constant__ CUtensorMap rmap, const float* __restr
     const int b = blockIdx.y;
     const ImgParams P = ip[b];
     if (it >= P.num_iter) return;
-
     constexpr int K2_UR = K2Rows<TY>::value, K2_ROWS = TY / K2_GW, K2_FW = K2Fill<TY>::warps, K2_THREADS = K2Fill<TY>::threads;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float* ut = reinterpret_cast<float*>(smem_raw);                       // [2][K2_UR][K2_US]
@@ -433,6 +432,18 @@ k_gradient_update(const __grid_constant__ CUtensorMap rmap, const float* __restr
     const int tx0 = (blockIdx.x % ntx) * K2_T, ty0 = (blockIdx.x / ntx) * TY;
     const InvXf* invb = inv + (size_t)b * N;
     const int nk = P.n_kept;
+    if (!WRITE_GRAD) {
+        // the epilogue's operands (x, optimizer slots) are asked into the L2 now, a whole copy loop before they are needed
+        constexpr int LINES = TY * (K2_T * 4 / 128);   // 128-byte lines per array per tile
+        for (int i = tid; i < 4 * LINES; i += K2Fill<TY>::threads) {
+            const int arr = i / LINES, l = i - arr * LINES, row = l / (K2_T * 4 / 128), seg = l - row * (K2_T * 4 / 128);
+            const int X = tx0 + 32 * seg, Y = ty0 + row;
+            if (X < W && Y < H) {
+                const float* base = arr == 0 ? x_cur : (arr == 1 ? s0 : (arr == 2 ? s1 : s2));
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(base + (size_t)b * H * W + (size_t)Y * W + X));
+            }
+        }
+    }
     K2_TM(0);
     if (tid == 0) {
 #pragma unroll
