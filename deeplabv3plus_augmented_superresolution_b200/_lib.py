@@ -65,6 +65,12 @@ SIGNATURES = {
                                           C.c_int, C.c_void_p, C.c_void_p]),
     "asr_warp_affine": (C.c_int, [C.c_void_p, _fp, _fp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p,
                                   C.c_void_p]),
+    "asr_backproject_workspace_bytes": (C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_size_t)]),
+    "asr_backproject_batched_ws": (C.c_int, [C.c_int, C.c_void_p, _fp, _fp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                             C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "asr_warp_affine_workspace_bytes": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_size_t)]),
+    "asr_warp_affine_ws": (C.c_int, [C.c_void_p, _fp, _fp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p,
+                                     C.c_void_p, C.c_size_t, C.c_void_p]),
     "asr_opm_extract": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p,
                                   C.c_void_p, C.c_void_p, C.c_void_p]),
     "asr_minmax_normalize": (C.c_int, [C.c_void_p, C.c_int64, C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p]),
@@ -172,6 +178,7 @@ class Workspace:
 
 
 _default_ws = Workspace()
+_aux_ws = Workspace()      # scratch of the warp / back-projection calls (kept apart from the solve's, which may be in use on the stream)
 
 
 def solve_batched(copies, angles, shifts, params, keep=None, want_loss: bool = False, workspace: Optional[Workspace] = None):

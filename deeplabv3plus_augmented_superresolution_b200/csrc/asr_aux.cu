@@ -617,14 +617,33 @@ extern "C" int asr_iou_counts(const int32_t* d_true, const int32_t* d_pred, int 
     return ASR_OK;
 }
 
-extern "C" int asr_warp_affine(const float* d_image, const float* h_angles, const float* h_shifts, int N, int H, int W,
-                               int C, int interp, float* d_out, void* stream) {
+static size_t warp_xf_bytes(int N) { return (sizeof(WarpXf) * (size_t)N + 255) / 256 * 256; }
+
+extern "C" int asr_warp_affine_workspace_bytes(int N, int H, int W, int C, size_t* bytes) {
+    if (!bytes) return fail(ASR_ENULL, "bytes is NULL");
+    if (N <= 0 || H <= 0 || W <= 0 || C <= 0 || C > K3_CMAX) return fail(ASR_EINVAL, "need N,H,W > 0 and 1 <= C <= %d", K3_CMAX);
+    *bytes = warp_xf_bytes(N) + sizeof(float4) * (size_t)H * W;   // per-copy transform table + the image padded to 4 channels
+    return ASR_OK;
+}
+
+static int warp_check(const float* d_image, const float* h_angles, const float* h_shifts, int N, int H, int W, int C, int interp,
+                      const float* d_out) {
     if (!d_image || !h_angles || !h_shifts || !d_out) return fail(ASR_ENULL, "null argument");
     if (N <= 0 || H <= 0 || W <= 0 || C <= 0 || C > K3_CMAX) return fail(ASR_EINVAL, "need N,H,W > 0 and 1 <= C <= %d", K3_CMAX);
     if (N > 65535) return fail(ASR_EINVAL, "N must be <= 65535");
     if (H > (1 << 20) || W > (1 << 20)) return fail(ASR_EINVAL, "image too large for the fp32 floor trick");
     if (interp != ASR_INTERP_NEAREST && interp != ASR_INTERP_BILINEAR) return fail(ASR_EINVAL, "unknown interpolation %d", interp);
     if (!aligned16(d_image) || !aligned16(d_out)) return fail(ASR_EINVAL, "device pointers must be 16-byte aligned");
+    return ASR_OK;
+}
+
+extern "C" int asr_warp_affine_ws(const float* d_image, const float* h_angles, const float* h_shifts, int N, int H, int W,
+                                  int C, int interp, float* d_out, void* d_workspace, size_t workspace_bytes, void* stream) {
+    if (int e = warp_check(d_image, h_angles, h_shifts, N, H, W, C, interp, d_out)) return e;
+    if (!d_workspace) return fail(ASR_ENULL, "null workspace");
+    if (reinterpret_cast<uintptr_t>(d_workspace) & 255u) return fail(ASR_EINVAL, "workspace must be 256-byte aligned");
+    const size_t npx = (size_t)H * W, xf_bytes = warp_xf_bytes(N);
+    if (workspace_bytes < xf_bytes + sizeof(float4) * npx) return fail(ASR_EWORKSPACE, "workspace %zu < required %zu bytes", workspace_bytes, xf_bytes + sizeof(float4) * npx);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     std::vector<WarpXf> xf(N);
     for (int k = 0; k < N; ++k) {
@@ -632,12 +651,7 @@ extern "C" int asr_warp_affine(const float* d_image, const float* h_angles, cons
         rotate_matrix(h_angles[k], H, W, r);
         xf[k] = WarpXf{r[0], r[1], r[2], r[3], r[4], r[5], -h_shifts[2 * k], -h_shifts[2 * k + 1]};
     }
-    // transient, stream-ordered scratch: the per-copy table and the image padded to 4 channels
-    const size_t npx = (size_t)H * W;
-    AsyncScratch guard;   // released in stream order on every return path
-    const size_t xf_bytes = (sizeof(WarpXf) * N + 255) / 256 * 256;
-    ASR_CUDA_TRY(guard.alloc(xf_bytes + sizeof(float4) * npx, st));
-    unsigned char* scratch = static_cast<unsigned char*>(guard.p);
+    unsigned char* scratch = static_cast<unsigned char*>(d_workspace);
     WarpXf* d_xf = reinterpret_cast<WarpXf*>(scratch);
     float4* d_pad = reinterpret_cast<float4*>(scratch + xf_bytes);
     ASR_CUDA_TRY(cudaMemcpyAsync(d_xf, xf.data(), sizeof(WarpXf) * N, cudaMemcpyHostToDevice, st));
@@ -651,6 +665,17 @@ extern "C" int asr_warp_affine(const float* d_image, const float* h_angles, cons
     }
     ASR_CUDA_TRY(cudaGetLastError());
     return ASR_OK;
+}
+
+// convenience form: the scratch is allocated and released in stream order inside the call
+extern "C" int asr_warp_affine(const float* d_image, const float* h_angles, const float* h_shifts, int N, int H, int W,
+                               int C, int interp, float* d_out, void* stream) {
+    if (int e = warp_check(d_image, h_angles, h_shifts, N, H, W, C, interp, d_out)) return e;
+    size_t need = 0;
+    if (int e = asr_warp_affine_workspace_bytes(N, H, W, C, &need)) return e;
+    AsyncScratch guard;   // released in stream order on every return path
+    ASR_CUDA_TRY(guard.alloc(need, static_cast<cudaStream_t>(stream)));
+    return asr_warp_affine_ws(d_image, h_angles, h_shifts, N, H, W, C, interp, d_out, guard.p, need, stream);
 }
 
 extern "C" int asr_opm_extract(const float* d_logits, int N, int h, int w, int K, int class_id, int mode,
@@ -710,12 +735,29 @@ extern "C" int asr_threshold(const float* d_x, int B, int64_t n, int32_t th_valu
     return ASR_OK;
 }
 
-extern "C" int asr_backproject_batched(int mode, const float* d_copies, const float* h_angles, const float* h_shifts, int B,
-                                       int N, int h, int w, int H, int W, float* d_out, void* stream) {
+static int backproject_check(int mode, const float* d_copies, const float* h_angles, const float* h_shifts, int B, int N, int h, int w,
+                             int H, int W, const float* d_out) {
     if (!d_copies || !h_angles || !h_shifts || !d_out) return fail(ASR_ENULL, "null argument");
     if (mode != ASR_BACKPROJECT_MAX && mode != ASR_BACKPROJECT_MEAN) return fail(ASR_EINVAL, "mode must be max or mean");
     if (B <= 0 || N <= 0 || h <= 0 || w <= 0 || H <= 0 || W <= 0 || B > 65535) return fail(ASR_EINVAL, "bad shape");
     if (!aligned16(d_copies) || !aligned16(d_out)) return fail(ASR_EINVAL, "device pointers must be 16-byte aligned");
+    return ASR_OK;
+}
+
+extern "C" int asr_backproject_workspace_bytes(int B, int N, size_t* bytes) {
+    if (!bytes) return fail(ASR_ENULL, "bytes is NULL");
+    if (B <= 0 || N <= 0) return fail(ASR_EINVAL, "bad shape");
+    *bytes = (sizeof(BackXf) * (size_t)B * N + 255) / 256 * 256;
+    return ASR_OK;
+}
+
+extern "C" int asr_backproject_batched_ws(int mode, const float* d_copies, const float* h_angles, const float* h_shifts, int B,
+                                          int N, int h, int w, int H, int W, float* d_out, void* d_workspace, size_t workspace_bytes,
+                                          void* stream) {
+    if (int e = backproject_check(mode, d_copies, h_angles, h_shifts, B, N, h, w, H, W, d_out)) return e;
+    if (!d_workspace) return fail(ASR_ENULL, "null workspace");
+    if (!aligned16(d_workspace)) return fail(ASR_EINVAL, "workspace must be 16-byte aligned");
+    if (workspace_bytes < sizeof(BackXf) * (size_t)B * N) return fail(ASR_EWORKSPACE, "workspace %zu < required %zu bytes", workspace_bytes, sizeof(BackXf) * (size_t)B * N);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     std::vector<BackXf> xf((size_t)B * N);
     for (size_t i = 0; i < xf.size(); ++i) {
@@ -724,9 +766,7 @@ extern "C" int asr_backproject_batched(int mode, const float* d_copies, const fl
         // tfa.image.translate(..., -shifts): transform offsets -(-dx), -(-dy)
         xf[i] = BackXf{r[0], r[1], r[2], r[3], r[4], r[5], -(-h_shifts[2 * i]), -(-h_shifts[2 * i + 1])};
     }
-    AsyncScratch scratch;   // released in stream order on every return path
-    ASR_CUDA_TRY(scratch.alloc(sizeof(BackXf) * xf.size(), st));
-    BackXf* d_xf = static_cast<BackXf*>(scratch.p);
+    BackXf* d_xf = static_cast<BackXf*>(d_workspace);
     ASR_CUDA_TRY(cudaMemcpyAsync(d_xf, xf.data(), sizeof(BackXf) * xf.size(), cudaMemcpyHostToDevice, st));
     if (H == 4 * h && W == 4 * w) {
         static unsigned long long attr = 0;
@@ -739,4 +779,15 @@ extern "C" int asr_backproject_batched(int mode, const float* d_copies, const fl
     }
     ASR_CUDA_TRY(cudaGetLastError());
     return ASR_OK;
+}
+
+// convenience form: the per-copy transform table is allocated and released in stream order inside the call
+extern "C" int asr_backproject_batched(int mode, const float* d_copies, const float* h_angles, const float* h_shifts, int B,
+                                       int N, int h, int w, int H, int W, float* d_out, void* stream) {
+    if (int e = backproject_check(mode, d_copies, h_angles, h_shifts, B, N, h, w, H, W, d_out)) return e;
+    size_t need = 0;
+    if (int e = asr_backproject_workspace_bytes(B, N, &need)) return e;
+    AsyncScratch scratch;   // released in stream order on every return path
+    ASR_CUDA_TRY(scratch.alloc(need, static_cast<cudaStream_t>(stream)));
+    return asr_backproject_batched_ws(mode, d_copies, h_angles, h_shifts, B, N, h, w, H, W, d_out, scratch.p, need, stream);
 }

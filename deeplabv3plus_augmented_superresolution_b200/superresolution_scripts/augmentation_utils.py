@@ -8,6 +8,7 @@ returning [N,h,w,K] logits as a NumPy array or a torch tensor.
 """
 from __future__ import annotations
 
+import ctypes as C
 import gc
 import os
 
@@ -45,9 +46,13 @@ def warp_copies(image, angles, shifts, interpolation="bilinear"):
     shf = np.ascontiguousarray(np.asarray(shifts, dtype=np.float32).reshape(-1, 2))
     n = ang.shape[0]
     out = torch.empty((n, H, W, Cc), dtype=torch.float32, device=img.device)
+    need = C.c_size_t()
+    _lib.check(L.asr_warp_affine_workspace_bytes(n, H, W, Cc, C.byref(need)))
+    ws = _lib._aux_ws.get(need.value, img.device)
     with torch.cuda.device(img.device):
-        _lib.check(L.asr_warp_affine(img.data_ptr(), ang.ctypes.data_as(_lib._fp), shf.ctypes.data_as(_lib._fp), n, H, W, Cc,
-                                     _lib.INTERP[interpolation.lower()], out.data_ptr(), _lib._stream_ptr(torch)))
+        _lib.check(L.asr_warp_affine_ws(img.data_ptr(), ang.ctypes.data_as(_lib._fp), shf.ctypes.data_as(_lib._fp), n, H, W, Cc,
+                                        _lib.INTERP[interpolation.lower()], out.data_ptr(), ws.data_ptr(), ws.numel(),
+                                        _lib._stream_ptr(torch)))
     return out
 
 

@@ -148,8 +148,11 @@ class Superresolution:
         out = torch.empty((B, H, W), dtype=torch.float32, device=copies.device)
         ang = _lib._host_f32(angles, (B, n))
         shf = _lib._host_f32(shifts, (B, n, 2))
+        need = C.c_size_t()
+        _lib.check(L.asr_backproject_workspace_bytes(B, n, C.byref(need)))
+        ws = _lib._aux_ws.get(need.value, copies.device)
         with torch.cuda.device(copies.device):
-            _lib.check(L.asr_backproject_batched(0 if mode == "max" else 1, copies.data_ptr(), ang.ctypes.data_as(_lib._fp),
-                                                 shf.ctypes.data_as(_lib._fp), B, n, h, w, H, W, out.data_ptr(),
-                                                 _lib._stream_ptr(torch)))
+            _lib.check(L.asr_backproject_batched_ws(0 if mode == "max" else 1, copies.data_ptr(), ang.ctypes.data_as(_lib._fp),
+                                                    shf.ctypes.data_as(_lib._fp), B, n, h, w, H, W, out.data_ptr(),
+                                                    ws.data_ptr(), ws.numel(), _lib._stream_ptr(torch)))
         return out

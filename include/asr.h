@@ -125,12 +125,23 @@ int asr_loss_grad_batched(const AsrSolveParams* params, int n_params,
 /* ---- superresolution.py:139-161  max_superresolution / mean_superresolution ----------------- */
 int asr_backproject_batched(int mode, const float* d_copies, const float* h_angles, const float* h_shifts,
                             int B, int N, int h, int w, int H, int W, float* d_out, void* stream);
+/* The same with a caller-owned workspace (the per-copy transform table) instead of a stream-ordered allocation inside
+ * the call: what a per-image loop should use.                                                                      */
+int asr_backproject_workspace_bytes(int B, int N, size_t* bytes);
+int asr_backproject_batched_ws(int mode, const float* d_copies, const float* h_angles, const float* h_shifts,
+                               int B, int N, int h, int w, int H, int W, float* d_out,
+                               void* d_workspace, size_t workspace_bytes, void* stream);
 
 /* ---- augmentation_utils.py:11-27  create_augmented_copies (rotate then translate) ------------
  * d_image [H,W,C] -> d_out [N,H,W,C]; also check_robustness.py:44-50 (interp NEAREST for labels).
  * angles/shifts are the already-drawn values: the RNG stays in Python (global NumPy stream).      */
 int asr_warp_affine(const float* d_image, const float* h_angles, const float* h_shifts, int N,
                     int H, int W, int C, int interp, float* d_out, void* stream);
+/* The same with a caller-owned workspace (transform table + the image padded to 4 channels). */
+int asr_warp_affine_workspace_bytes(int N, int H, int W, int C, size_t* bytes);
+int asr_warp_affine_ws(const float* d_image, const float* h_angles, const float* h_shifts, int N,
+                       int H, int W, int C, int interp, float* d_out,
+                       void* d_workspace, size_t workspace_bytes, void* stream);
 
 /* ---- augmentation_utils.py:80-115 + utils.py:115-119  OPM extraction ------------------------
  * d_logits [N,h,w,K] NHWC -> d_class_out [N,h,w]; d_max_out [N,h,w] only for SLICE_MAX.

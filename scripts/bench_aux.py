@@ -41,6 +41,14 @@ for mode in ("argmax", "slice", "slice_max"):
     ms = timeit(lambda: AU.extract_opm(logits, 8, mode))
     b = logits.numel() * 4 * (2 if mode == "slice" else 1) + N * 128 * 128 * 4 * (2 if mode == "slice_max" else 1)
     out[f"opm_{mode}"] = {"ms": ms, "algorithmic_bytes": b, "GBps": b / ms / 1e6, "frac_hbm": b / ms / 1e6 / peak}
+# the same OPM extraction for 8 images' worth of predictions in one launch (the batch_runner shape): at 100 copies the kernel is
+# launch-latency sized (~40 us), the bandwidth fraction only means something with more work per launch
+logits8 = torch.randn((8 * N, 128, 128, 21), device="cuda", generator=g)
+for mode in ("argmax", "slice", "slice_max"):
+    ms = timeit(lambda: AU.extract_opm(logits8, 8, mode))
+    b = logits8.numel() * 4 * (2 if mode == "slice" else 1) + 8 * N * 128 * 128 * 4 * (2 if mode == "slice_max" else 1)
+    out[f"opm_{mode}_800copies"] = {"ms": ms, "algorithmic_bytes": b, "GBps": b / ms / 1e6, "frac_hbm": b / ms / 1e6 / peak}
+del logits8
 copies, a2, s2 = make_augmented_copies(8, N, device="cuda")
 stack = copies[0, :, :, :, None].contiguous()
 ms = timeit(lambda: SU._normalize_stack_device(stack))

@@ -461,3 +461,97 @@ def test_misaligned_pointers_are_rejected():
     rc = L.asr_solve_batched(arr, n, copies.data_ptr(), a32.ctypes.data_as(fp), s32.ctypes.data_as(fp), None, 1, 3, 16, 16, 64, 64,
                              x.data_ptr(), None, base + 16, need.value, None)
     assert rc == -1 and b"aligned" in L.asr_last_error()
+
+
+# --------------------------------------------------------------------------------------------------
+# paths VERDICT r01 listed as untested: generic back-projection, per-image normalisation, chunked copies, workspace forms
+# --------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("mode", ["max", "mean"])
+@pytest.mark.parametrize("sizes", [((32, 32), (64, 64)), ((24, 40), (72, 120)), ((16, 16), (128, 128))])
+def test_backproject_generic_scale(mode, sizes):
+    """Superresolution's default feature_size (64,64) -> (512,512) is a x8 back-projection (superresolution.py:28,139-161):
+    any output/feature ratio other than 4 takes the one-thread-per-pixel kernel."""
+    from deeplabv3plus_augmented_superresolution_b200.superresolution_scripts.optimizer import Optimizer
+    from deeplabv3plus_augmented_superresolution_b200.superresolution_scripts.superresolution import Superresolution
+    (h, w), (H, W) = sizes
+    from deeplabv3plus_augmented_superresolution_b200.synthetic import make_augmented_copies
+    copies, ang, sh = make_augmented_copies(2, 7, (h, w), (H, W), 0.4, 0.2 * W, seed=31, device="cuda")
+    copies = copies + 0.25 * torch.rand_like(copies)
+    s = Superresolution(1, 0.3, 0.7, 0, optimizer=Optimizer(), feature_size=(h, w), output_size=(H, W))
+    out = s.backproject_batched(copies, ang, sh, mode)
+    for b in range(2):
+        np.testing.assert_array_equal(out[b].cpu().numpy(), O.backproject(copies[b].cpu().numpy(), ang[b], sh[b], mode, (H, W))[..., 0])
+
+
+def test_load_sr_data_per_image_normalisation(tmp_path):
+    """global_normalize=False: every copy is normalised with its own min/max (superres_utils.py:56-62 with global_min=None)."""
+    from deeplabv3plus_augmented_superresolution_b200 import hdf5_lite
+    from deeplabv3plus_augmented_superresolution_b200.superresolution_scripts import superres_utils as SU
+    rng = np.random.RandomState(9)
+    cm = [(rng.randn(16, 16, 1) * (k + 1) + k).astype(np.float32) for k in range(6)]
+    cm[3][:] = 2.0                                                    # constant copy: max == min -> denominator 1 -> all zeros
+    mm = [(rng.rand(16, 16, 1) * 5).astype(np.float32) for _ in range(6)]
+    f = hdf5_lite.File(str(tmp_path / "2007_000033.hdf5"), "w")
+    f.create_dataset("class_masks", data=cm); f.create_dataset("max_masks", data=mm)
+    f.create_dataset("angles", data=np.zeros(6, np.float32)); f.create_dataset("shifts", data=np.zeros((6, 2), np.float32))
+    f.attrs["filename"] = "2007_000033"; f.attrs["mode"] = "slice_max"; f.attrs["angle_max"] = 0.15; f.attrs["shift_max"] = 80
+    f.close()
+    c, m, a, s, name = SU.load_SR_data(str(tmp_path / "2007_000033.hdf5"), num_aug=5, global_normalize=False)
+    assert c.shape == (5, 16, 16, 1) and m.shape == (5, 16, 16, 1) and name == "2007_000033"
+    for k in range(5):
+        np.testing.assert_array_equal(c[k].cpu().numpy(), SU.min_max_normalization(cm[k], 0.0, 1.0).astype(np.float32))
+        np.testing.assert_array_equal(c[k].cpu().numpy(), O.minmax_normalize_global(cm[k][None])[0])
+        np.testing.assert_array_equal(m[k].cpu().numpy(), O.minmax_normalize_global(mm[k][None])[0])
+    assert (c[3] == 0).all()
+    cg, _, _, _, _ = SU.load_SR_data(str(tmp_path / "2007_000033.hdf5"), num_aug=5, global_normalize=True)
+    np.testing.assert_array_equal(cg.cpu().numpy(), O.minmax_normalize_global(np.stack(cm[:5])))
+    # slice mode: no normalisation at all (superres_utils.py:186)
+    f = hdf5_lite.File(str(tmp_path / "2007_000034.hdf5"), "w")
+    f.create_dataset("class_masks", data=cm); f.create_dataset("angles", data=np.zeros(6, np.float32))
+    f.create_dataset("shifts", data=np.zeros((6, 2), np.float32))
+    f.attrs["filename"] = "2007_000034"; f.attrs["mode"] = "slice"; f.attrs["angle_max"] = 0.15; f.attrs["shift_max"] = 80
+    f.close()
+    c2, m2, _, _, _ = SU.load_SR_data(str(tmp_path / "2007_000034.hdf5"), num_aug=6)
+    assert m2 is None
+    np.testing.assert_array_equal(c2.cpu().numpy(), np.stack(cm))
+
+
+def test_create_augmented_copies_chunked():
+    from deeplabv3plus_augmented_superresolution_b200.superresolution_scripts import augmentation_utils as AU
+    img = np.random.RandomState(1).rand(40, 48, 3).astype(np.float32)
+    np.random.seed(77)
+    whole, a1, s1 = AU.create_augmented_copies(img, 12, 0.3, 10)
+    np.random.seed(77)
+    chunks, a2, s2 = AU.create_augmented_copies_chunked(img, 12, 0.3, 10, chunk_size=4)
+    assert isinstance(chunks, np.ndarray) and chunks.shape == (12, 40, 48, 3)
+    np.testing.assert_array_equal(a1, a2); np.testing.assert_array_equal(s1, s2)
+    np.testing.assert_array_equal(whole.cpu().numpy(), chunks)
+    with pytest.raises(Exception, match="multiple"):
+        AU.create_augmented_copies_chunked(img, 10, 0.3, 10, chunk_size=4)
+
+
+def test_workspace_forms_of_aux_calls():
+    """asr_warp_affine_ws / asr_backproject_batched_ws give the results of the allocating forms and check their workspace."""
+    L = A.lib()
+    fp = C.POINTER(C.c_float)
+    img = torch.rand((48, 64, 3), device="cuda")
+    ang = np.array([0.0, 0.2, -0.1], np.float32); shf = np.array([[0, 0], [5.5, -3], [-8, 2.25]], np.float32)
+    need = C.c_size_t()
+    A.check(L.asr_warp_affine_workspace_bytes(3, 48, 64, 3, C.byref(need)))
+    ws = torch.empty(need.value, dtype=torch.uint8, device="cuda")
+    o1 = torch.empty((3, 48, 64, 3), device="cuda"); o2 = torch.empty_like(o1)
+    A.check(L.asr_warp_affine_ws(img.data_ptr(), ang.ctypes.data_as(fp), shf.ctypes.data_as(fp), 3, 48, 64, 3, 1, o1.data_ptr(), ws.data_ptr(), need.value, None))
+    A.check(L.asr_warp_affine(img.data_ptr(), ang.ctypes.data_as(fp), shf.ctypes.data_as(fp), 3, 48, 64, 3, 1, o2.data_ptr(), None))
+    torch.cuda.synchronize()
+    assert torch.equal(o1, o2)
+    assert L.asr_warp_affine_ws(img.data_ptr(), ang.ctypes.data_as(fp), shf.ctypes.data_as(fp), 3, 48, 64, 3, 1, o1.data_ptr(), ws.data_ptr(), need.value - 1, None) == -5
+    copies, a2, s2 = synth(2, 5, (16, 16), 0.3, 8, seed=41)
+    a32, s32 = np.ascontiguousarray(a2, np.float32), np.ascontiguousarray(s2, np.float32)
+    A.check(L.asr_backproject_workspace_bytes(2, 5, C.byref(need)))
+    ws = torch.empty(need.value, dtype=torch.uint8, device="cuda")
+    b1 = torch.empty((2, 64, 64), device="cuda"); b2 = torch.empty_like(b1)
+    A.check(L.asr_backproject_batched_ws(1, copies.data_ptr(), a32.ctypes.data_as(fp), s32.ctypes.data_as(fp), 2, 5, 16, 16, 64, 64, b1.data_ptr(), ws.data_ptr(), need.value, None))
+    A.check(L.asr_backproject_batched(1, copies.data_ptr(), a32.ctypes.data_as(fp), s32.ctypes.data_as(fp), 2, 5, 16, 16, 64, 64, b2.data_ptr(), None))
+    torch.cuda.synchronize()
+    assert torch.equal(b1, b2)
+    assert L.asr_backproject_batched_ws(1, copies.data_ptr(), a32.ctypes.data_as(fp), s32.ctypes.data_as(fp), 2, 5, 16, 16, 64, 64, b1.data_ptr(), ws.data_ptr(), 8, None) == -5
