@@ -1029,7 +1029,7 @@ static int configure_kernels() {
     ASR_CUDA_TRY(cudaFuncSetAttribute(k_forward_residual<K1_XR_SMALL, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k1_smem<K1_XR_SMALL>()));
     ASR_CUDA_TRY(cudaFuncSetAttribute(k_forward_residual<K1_XR_BIG, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k1_smem<K1_XR_BIG>()));
 #define ASR_K2_ATTR(WG, BT, TY) \
-    ASR_CUDA_TRY(cudaFuncSetAttribute(k_gradient_update<WG, BT, TY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k2_smem<TY>()));
+    ASR_CUDA_TRY(cudaFuncSetAttribute(k_gradient_update<WG, BT, TY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(k2_smem<TY>())));
 #define ASR_K2_ATTRS(TY) ASR_K2_ATTR(false, false, TY) ASR_K2_ATTR(false, true, TY) ASR_K2_ATTR(true, false, TY) ASR_K2_ATTR(true, true, TY)
     ASR_K2_ATTRS(64) ASR_K2_ATTRS(32)
 #undef ASR_K2_ATTRS
@@ -1144,26 +1144,42 @@ static int solve_impl(const AsrSolveParams* params, int n_params, const float* d
     ASR_LAUNCH(k_tap_tables, dim3((4 * (w + h + 4 * K2_TPAD) + 255) / 256, N, B), 256, 0, st, D.inv, D.tapc, D.tapr, N, h, w, H, W);
     ASR_LAUNCH(k_forward_tables, dim3((t1 + w + h + 127) / 128, T.max_kept, B), 128, 0, st, D.fwd, D.src, D.ip, D.fcp, D.fcolw, D.froww,
                D.boxd, N, h, w, H, W, ntj, nti, box_rows);
+    // one launch group = the images [b0, b0+nb) that go through every kernel launch together
+    struct Group { int b0, nb, iters, min_iters, ty; bool uniform_kept; };
+    auto make_group = [&](int b0, int nb) {
+        Group G{b0, nb, 0, INT_MAX, k2_tile_height(nb, H, W), true};   // uniform_kept: every image keeps max_kept copies, no K1 CTA is idle
+        for (int b = b0; b < b0 + nb; ++b) {
+            G.iters = T.hp[b].num_iter > G.iters ? T.hp[b].num_iter : G.iters;
+            G.min_iters = T.hp[b].num_iter < G.min_iters ? T.hp[b].num_iter : G.min_iters;
+            G.uniform_kept = G.uniform_kept && T.ip[b].n_kept == T.max_kept;
+        }
+        return G;
+    };
+    auto launch_k1 = [&](const Group& G, int it, cudaStream_t s) -> int {
+        const size_t ro = (size_t)G.b0 * N * h * wp, so = (size_t)G.b0 * N;
+        ASR_LAUNCH_K1(T.small_box, t1, T.max_kept, G.nb, s, (it & 1) ? map_b : map_a, d_copies, D.resid + ro, D.fcp + so, D.fcolw + so * w,
+                      D.froww + so * h, D.boxd + so * t1, D.ip + G.b0, it, (!G.uniform_kept || it >= G.min_iters) ? 1 : 0, N, h, w, wp, ntj,
+                      div_magic(ntj), G.b0);
+        return ASR_OK;
+    };
+    auto launch_k2 = [&](const Group& G, int it, cudaStream_t s) -> int {
+        const size_t po = (size_t)G.b0 * plane;
+        float* xc = ((it & 1) ? D.xb : D.xa) + po;
+        float* xn = ((it & 1) ? D.xa : D.xb) + po;
+        ASR_LAUNCH_K2(false, T.any_btv, G.ty, H, W, G.nb, s, map_r, xc, xn, D.s0 + po, D.s1 + po, D.s2 + po, D.tapc, D.tapr,
+                      D.inv + (size_t)G.b0 * N, D.ip + G.b0, D.sched + G.b0, it, N, h, w, H, W, B, G.b0);
+        return ASR_OK;
+    };
     int group = params[0].images_in_flight > 0 ? params[0].images_in_flight : B;
+    // (Two halves of a group on two streams, half an iteration apart, so that K1 of one half shares the SMs with K2 of the other:
+    //  measured +1.3 % with the kernels as they are and -16 % when K2 is held to one CTA per SM to make room -- both kernels are
+    //  issue-heavy, there is little idle capacity to trade.  scripts/dev/dual_stream_experiment.sh, DESIGN.md.)
     for (int b0 = 0; b0 < B; b0 += group) {
         const int nb = (B - b0 < group) ? B - b0 : group;
-        int iters = 0, min_iters = INT_MAX;
-        bool uniform_kept = true;   // every image of the group keeps max_kept copies: no CTA of the K1 grid is idle
-        for (int b = b0; b < b0 + nb; ++b) {
-            iters = T.hp[b].num_iter > iters ? T.hp[b].num_iter : iters;
-            min_iters = T.hp[b].num_iter < min_iters ? T.hp[b].num_iter : min_iters;
-            uniform_kept = uniform_kept && T.ip[b].n_kept == T.max_kept;
-        }
-        const size_t po = (size_t)b0 * plane, ro = (size_t)b0 * N * h * wp, so = (size_t)b0 * N;
-        const int ty = k2_tile_height(nb, H, W);
-        for (int it = 0; it < iters; ++it) {
-            float* xc = ((it & 1) ? D.xb : D.xa) + po;
-            float* xn = ((it & 1) ? D.xa : D.xb) + po;
-            ASR_LAUNCH_K1(T.small_box, t1, T.max_kept, nb, st, (it & 1) ? map_b : map_a, d_copies, D.resid + ro, D.fcp + so, D.fcolw + so * w,
-                          D.froww + so * h, D.boxd + so * t1, D.ip + b0, it, (!uniform_kept || it >= min_iters) ? 1 : 0, N, h, w, wp, ntj,
-                          div_magic(ntj), b0);
-            ASR_LAUNCH_K2(false, T.any_btv, ty, H, W, nb, st, map_r, xc, xn, D.s0 + po, D.s1 + po, D.s2 + po, D.tapc, D.tapr,
-                          D.inv + (size_t)b0 * N, D.ip + b0, D.sched + b0, it, N, h, w, H, W, B, b0);
+        const Group G = make_group(b0, nb);
+        for (int it = 0; it < G.iters; ++it) {
+            if (int e = launch_k1(G, it, st)) return e;
+            if (int e = launch_k2(G, it, st)) return e;
         }
     }
     ASR_CUDA_TRY(cudaGetLastError());
