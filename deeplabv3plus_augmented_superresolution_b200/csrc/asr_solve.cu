@@ -87,16 +87,19 @@ __global__ void k_init_upsample(const float* __restrict__ copies, const ImgParam
 // descriptor load and the TMA issue (round 1 recomputed boxes and tables in every CTA of every iteration:
 // half of the kernel's instructions).
 constexpr int K1_TJ = 16;              // LR tile: 16 cells wide ...
-constexpr int K1_TI = 12;              // ... 12 cells tall = 192 cells, one per thread in the second phase
-constexpr int K1_THREADS = 192;        // 48 p-columns x 4 row groups of 9 rows
+constexpr int K1_TI = 16;              // ... 16 cells tall = 256 cells, one per thread in the second phase.  (Round 1's 16x12 tile gave every
+                                       // gather thread 9 rows = 4 packed pairs + one scalar row that cost almost a pair, and tiled a 128-row map
+                                       // with 11 x 12 = 132 rows; 16 rows = 6 packed pairs per thread and no ragged tile: K1 23.9 -> see DESIGN.md)
+constexpr int K1_THREADS = 256;
+constexpr int K1_GATHER = 192;         // threads of the gather phase: 48 p-columns x 4 row groups of 12 rows
 constexpr int K1_PC = 3 * K1_TJ;       // needed p columns (48) and rows (36) per tile
 constexpr int K1_PR = 3 * K1_TI;
 constexpr int K1_PBS = K1_PC;          // p buffer stride 48: 3 rows = 144 = 16 (mod 32) floats, so the two cell rows a warp reads in
                                        // the second phase land on complementary bank sets (stride 49 collided on one bank: 2 wavefronts per load)
 constexpr int K1_XS = 96;              // TMA box width (floats): 62*sqrt(2)+2+3 < 96, multiple of 32 (a pitch of 80 = 16 mod 32 saves TMA
                                        // bytes for small rotations but adds conflicts across source rows: measured 29.5 vs 28.0 us)
-constexpr int K1_XR_SMALL = 60;        // TMA box height when 62|sin|+46|cos|+3 <= 60 for every copy (|angle| <~ 0.19 rad): 7 CTAs/SM
-constexpr int K1_XR_BIG = 84;          // ... for any rotation: sqrt(62^2+46^2)+3 < 84: 5 CTAs/SM
+constexpr int K1_XR_SMALL = 76;        // TMA box height when 62|sin|+62|cos|+3 <= 76 for every copy (|angle| <~ 0.19 rad): 5 CTAs/SM
+constexpr int K1_XR_BIG = 92;          // ... for any rotation: 62*sqrt(2)+3 < 92: 4 CTAs/SM
 constexpr int K1_SPAN_X = 4 * (K1_TJ - 1) + 2, K1_SPAN_Y = 4 * (K1_TI - 1) + 2;   // last needed p position = first + SPAN
 constexpr int K1_EMPTY = INT_MIN;      // BoxDesc.by0 of a (tile, copy) whose rotated image is all zero
 template <int XR>
@@ -167,13 +170,7 @@ __global__ void k_forward_tables(const FwdXf* __restrict__ fwd, const int* __res
     }
 }
 
-// Two thread maps for the gather phase (the second phase is always one cell per thread):
-//   CF = false  block (48, 4): thread = p column x group of 9 rows (4 packed row pairs + 1 scalar row).  32 consecutive needed
-//               columns span 42 source pixels (the resize reads 3 of every 4), so every tap load has 2-way bank conflicts.
-//   CF = true   block (32, 6): warp = half a p row (24 needed columns = 31 source pixels: conflict-free, 24 of 32 lanes
-//               active) x a third of the rows; thread = 12 rows = 6 packed pairs, no scalar row.  Same instruction count
-//               per CTA (fewer per-row instructions pay for the idle lanes), 37 % fewer shared-memory wavefronts.
-template <int XR, bool CF>
+template <int XR>
 __global__ void __launch_bounds__(K1_THREADS)
 k_forward_residual(const __grid_constant__ CUtensorMap xmap, const float* __restrict__ copies, float* __restrict__ resid,
                    const FwdCopy* __restrict__ fcp, const float4* __restrict__ fcolw, const float4* __restrict__ froww,
@@ -188,11 +185,13 @@ k_forward_residual(const __grid_constant__ CUtensorMap xmap, const float* __rest
     float* pb = xt + K1_XS * XR;                                                 // [K1_PR][K1_PBS]
     int* boxs = reinterpret_cast<int*>(pb + K1_PR * K1_PBS);                     // bx0a, by0
 
-    // gather phase: p column, first p row, first q-row offset of this thread; the linear id maps to one LR cell in the second phase
-    const int pcn = CF ? 24 * (threadIdx.y & 1) + threadIdx.x : threadIdx.x;
-    const int prow0 = CF ? 12 * (threadIdx.y >> 1) : 9 * threadIdx.y, qrow0 = CF ? 16 * (threadIdx.y >> 1) : 12 * threadIdx.y;
-    const bool gathers = !CF || threadIdx.x < 24;
-    const int tid = threadIdx.y * blockDim.x + threadIdx.x;
+    // gather phase (threads 0..191): p column and row group of 12 rows = 4 cell rows; the thread id maps to one LR cell in the second phase.
+    // (A conflict-free map -- 24 of 32 lanes active, half a p row per warp -- was measured slower: 24.7 vs 23.9 us, it trades 37 % of the
+    //  shared-memory wavefronts for 15 % more instructions and the kernel is as much issue- as shared-memory bound.)
+    const int tid = threadIdx.x;
+    const int g = tid / K1_PC, pcn = tid - g * K1_PC;
+    const int prow0 = 12 * g, qrow0 = 16 * g;
+    const bool gathers = tid < K1_GATHER;
     const unsigned slot = (unsigned)b * (unsigned)N + (unsigned)ks;              // B*N*max(h,w,tiles) < 2^32 is checked on the host
     if (tid == 0) {
         const BoxDesc d = boxd[(size_t)slot * gridDim.x + blockIdx.x];
@@ -222,7 +221,7 @@ k_forward_residual(const __grid_constant__ CUtensorMap xmap, const float* __rest
     if (!empty && gathers) {
         // ---- p = rotate-gather of x at the needed integer positions ------------------------------
         const float qxf = (float)(qx_lo + pcn + pcn / 3);         // 4*(pcn/3) + pcn%3
-        const float qy0 = (float)(qy_lo + qrow0);                 // first row of the thread; rows qy0 + {0,1,2,4,5,6,8,9,10,(12,13,14)}
+        const float qy0 = (float)(qy_lo + qrow0);                 // first row of the thread; rows qy0 + {0,1,2,4,5,6,8,9,10,12,13,14}
         const float ax = fmul(T.r0, qxf), ay = fmul(T.r3, qxf);
         // byte address of tap (y0,x0) = 4*(y0*XS + x0) + cst, box origin and tile address folded into cst
         const int cst = (int)smem_u32(xt) - 4 * (boxs[1] * K1_XS + boxs[0]);
@@ -236,7 +235,7 @@ k_forward_residual(const __grid_constant__ CUtensorMap xmap, const float* __rest
         // two rows of the column travel as the two lanes of packed fp32 instructions (asr_common.cuh); the row
         // coordinates are small integers, so qy0 + offset is exact and equals the literal (float)qy
 #pragma unroll
-        for (int m = 0; m < (CF ? 12 : 8); m += 2) {
+        for (int m = 0; m < 12; m += 2) {
             const int o0 = 4 * (m / 3) + m % 3, o1 = 4 * ((m + 1) / 3) + (m + 1) % 3;
             const f32x2 qy2 = add2(qy0p, pk((float)o0, (float)o1));
             const f32x2 ix = add2(sum2(axp, mul2(r1p, qy2)), r2p);      // fl(fl(fl(r0*qx) + fl(r1*qy)) + r2)
@@ -253,15 +252,6 @@ k_forward_residual(const __grid_constant__ CUtensorMap xmap, const float* __rest
                                     pk(lds_tap<4 * K1_XS + 4>(ta), lds_tap<4 * K1_XS + 4>(tb)), wx0, wx1, wy0, wy1);
             prow[m * K1_PBS] = pk_lo(o);
             prow[(m + 1) * K1_PBS] = pk_hi(o);
-        }
-        if (!CF) {   // the ninth row
-            const float qy = fadd(qy0, 10.0f);
-            const float ix = fadd(fadd(ax, fmul(T.r1, qy)), T.r2), iy = fadd(fadd(ay, fmul(T.r4, qy)), T.r5);
-            const Floor fx = floor_magic(ix), fy = floor_magic(iy);
-            const float wx1 = fsub(ix, fx.f), wx0 = fsub(1.0f, wx1);
-            const float wy1 = fsub(iy, fy.f), wy0 = fsub(1.0f, wy1);
-            const unsigned t0 = (unsigned)cst + 4u * ((unsigned)(fy.raw - kMagicBits) * K1_XS + (unsigned)(fx.raw - kMagicBits));
-            prow[8 * K1_PBS] = bilerp(lds_tap<0>(t0), lds_tap<4>(t0), lds_tap<4 * K1_XS>(t0), lds_tap<4 * K1_XS + 4>(t0), wx0, wx1, wy0, wy1);
         }
     }
     __syncthreads();
@@ -900,8 +890,8 @@ static void build_tables(const AsrSolveParams* params, int n_params, const float
             invert_transform(tr, tri);
             const size_t o = (size_t)b * N + kept;
             T.fwd[o] = FwdXf{rot[0], rot[1], rot[2], rot[3], rot[4], rot[5], tr[2], tr[5]};
-            // K1 box rows <= 62|t3| + 46|t4| + 3 (corner span of the 63x47 p region, the +1 tap, floor); small margin
-            if (62.0f * fabsf(rot[3]) + 46.0f * fabsf(rot[4]) + 3.05f > (float)K1_XR_SMALL) T.small_box = false;
+            // K1 box rows <= 62|t3| + 62|t4| + 3 (corner span of the 63x63 p region, the +1 tap, floor); small margin
+            if ((float)K1_SPAN_X * fabsf(rot[3]) + (float)K1_SPAN_Y * fabsf(rot[4]) + 3.05f > (float)K1_XR_SMALL) T.small_box = false;
             T.inv[o] = InvXf{roti[0], roti[1], roti[2], roti[3], roti[4], roti[5], tri[2], tri[5]};
             T.src[o] = k;
             ++kept;
@@ -1024,10 +1014,8 @@ static unsigned div_magic(int d) { return (unsigned)((0x100000000ull + (unsigned
 static int configure_kernels() {
     static unsigned long long done = 0;   // one bit per device: the attribute belongs to the (function, device) pair
     if (!first_use_on_device(&done)) return ASR_OK;
-    ASR_CUDA_TRY(cudaFuncSetAttribute(k_forward_residual<K1_XR_SMALL, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k1_smem<K1_XR_SMALL>()));
-    ASR_CUDA_TRY(cudaFuncSetAttribute(k_forward_residual<K1_XR_BIG, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k1_smem<K1_XR_BIG>()));
-    ASR_CUDA_TRY(cudaFuncSetAttribute(k_forward_residual<K1_XR_SMALL, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k1_smem<K1_XR_SMALL>()));
-    ASR_CUDA_TRY(cudaFuncSetAttribute(k_forward_residual<K1_XR_BIG, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k1_smem<K1_XR_BIG>()));
+    ASR_CUDA_TRY(cudaFuncSetAttribute(k_forward_residual<K1_XR_SMALL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k1_smem<K1_XR_SMALL>()));
+    ASR_CUDA_TRY(cudaFuncSetAttribute(k_forward_residual<K1_XR_BIG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k1_smem<K1_XR_BIG>()));
 #define ASR_K2_ATTR(WG, BT, TY) \
     ASR_CUDA_TRY(cudaFuncSetAttribute(k_gradient_update<WG, BT, TY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(k2_smem<TY>())));
 #define ASR_K2_ATTRS(TY) ASR_K2_ATTR(false, false, TY) ASR_K2_ATTR(false, true, TY) ASR_K2_ATTR(true, false, TY) ASR_K2_ATTR(true, true, TY)
@@ -1089,21 +1077,10 @@ static int k2_tile_height(int n_images, int H, int W) {
         }                                                                                                             \
     } while (0)
 
-static bool k1_conflict_free() {   // ASR_K1_CF=1 selects the conflict-free 32x6 thread map (measured slower: 24.7 vs 23.9 us, more instructions)
-    const char* e = getenv("ASR_K1_CF");
-    return e && e[0] == '1';
-}
-#define ASR_LAUNCH_K1_V(XR, CF, bdim, t1, nk, nimg, st, ...) \
-    ASR_LAUNCH_TIMED(0, (k_forward_residual<XR, CF>), dim3(t1, nk, nimg), bdim, k1_smem<XR>(), st, __VA_ARGS__)
-#define ASR_LAUNCH_K1(small, t1, nk, nimg, st, ...)                                                                  \
-    do {                                                                                                             \
-        if (k1_conflict_free()) {                                                                                    \
-            if (small) ASR_LAUNCH_K1_V(K1_XR_SMALL, true, dim3(32, 6), t1, nk, nimg, st, __VA_ARGS__);               \
-            else ASR_LAUNCH_K1_V(K1_XR_BIG, true, dim3(32, 6), t1, nk, nimg, st, __VA_ARGS__);                       \
-        } else {                                                                                                     \
-            if (small) ASR_LAUNCH_K1_V(K1_XR_SMALL, false, dim3(48, 4), t1, nk, nimg, st, __VA_ARGS__);              \
-            else ASR_LAUNCH_K1_V(K1_XR_BIG, false, dim3(48, 4), t1, nk, nimg, st, __VA_ARGS__);                      \
-        }                                                                                                            \
+#define ASR_LAUNCH_K1(small, t1, nk, nimg, st, ...)                                                                                     \
+    do {                                                                                                                                \
+        if (small) ASR_LAUNCH_TIMED(0, k_forward_residual<K1_XR_SMALL>, dim3(t1, nk, nimg), K1_THREADS, k1_smem<K1_XR_SMALL>(), st, __VA_ARGS__); \
+        else ASR_LAUNCH_TIMED(0, k_forward_residual<K1_XR_BIG>, dim3(t1, nk, nimg), K1_THREADS, k1_smem<K1_XR_BIG>(), st, __VA_ARGS__);           \
     } while (0)
 
 static int solve_impl(const AsrSolveParams* params, int n_params, const float* d_copies, const float* h_angles,
