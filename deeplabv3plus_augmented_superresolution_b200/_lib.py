@@ -181,14 +181,16 @@ _default_ws = Workspace()
 _aux_ws = Workspace()      # scratch of the warp / back-projection calls (kept apart from the solve's, which may be in use on the stream)
 
 
-def solve_batched(copies, angles, shifts, params, keep=None, want_loss: bool = False, workspace: Optional[Workspace] = None):
+def solve_batched(copies, angles, shifts, params, keep=None, want_loss: bool = False, workspace: Optional[Workspace] = None,
+                  output_size=None):
     """asr_solve_batched.  copies: CUDA float32 tensor [B,N,h,w]; angles [B,N], shifts [B,N,2] host arrays;
-    params: SolveParams or a list of B of them.  Returns x [B,4h,4w] (CUDA) and, if asked, loss [B] (CUDA)."""
+    params: SolveParams or a list of B of them; output_size (H, W) defaults to (4h, 4w), the reference callers' shape (any even
+    integer ratio is accepted).  Returns x [B,H,W] (CUDA) and, if asked, loss [B] (CUDA)."""
     torch = _torch()
     L = lib()
     assert copies.is_cuda and copies.dtype == torch.float32 and copies.is_contiguous() and copies.dim() == 4
     B, N, h, w = copies.shape
-    H, W = 4 * h, 4 * w
+    H, W = (4 * h, 4 * w) if output_size is None else (int(output_size[0]), int(output_size[1]))
     ang = _host_f32(angles, (B, N))
     shf = _host_f32(shifts, (B, N, 2))
     kp = None if keep is None else np.ascontiguousarray(np.asarray(keep, dtype=np.uint8).reshape(B, N))
@@ -208,12 +210,12 @@ def solve_batched(copies, angles, shifts, params, keep=None, want_loss: bool = F
 
 
 def loss_grad_batched(x, copies, angles, shifts, params, keep=None, workspace: Optional[Workspace] = None):
-    """asr_loss_grad_batched: one evaluation of residual, gradient and loss at x [B,H,W]."""
+    """asr_loss_grad_batched: one evaluation of residual, gradient and loss at x [B,H,W] (H, W taken from x)."""
     torch = _torch()
     L = lib()
     B, N, h, w = copies.shape
-    H, W = 4 * h, 4 * w
-    assert x.shape == (B, H, W) and x.is_cuda and x.is_contiguous() and copies.is_contiguous()
+    H, W = int(x.shape[1]), int(x.shape[2])
+    assert x.shape[0] == B and x.is_cuda and x.is_contiguous() and copies.is_contiguous()
     ang = _host_f32(angles, (B, N))
     shf = _host_f32(shifts, (B, N, 2))
     kp = None if keep is None else np.ascontiguousarray(np.asarray(keep, dtype=np.uint8).reshape(B, N))

@@ -389,6 +389,54 @@ __global__ void k_tap_tables(const InvXf* __restrict__ inv, float2* __restrict__
     }
 }
 
+// One optimizer step on one pixel in TensorFlow's expression order (ApplyAdam[WithAmsgrad], ApplyAdagradV2, ApplyAdadelta,
+// ApplyAdaMax, ApplyGradientDescent, ApplyKerasMomentum): slots o0,o1,o2 in, updated slots written to s0,s1,s2[gi].
+__device__ __forceinline__ float optimizer_step(const ImgParams& P, const Sched sc, float g, float xi, float o0, float o1, float o2,
+                                                size_t gi, float* __restrict__ s0, float* __restrict__ s1, float* __restrict__ s2) {
+    float xn;
+    switch (P.optimizer) {
+    case ASR_OPT_SGD:
+        if (P.momentum == 0.0f) {
+            xn = fsub(xi, fmul(sc.x, g));
+        } else {
+            const float a = fsub(fmul(o0, P.momentum), fmul(sc.x, g));
+            s0[gi] = a;
+            xn = P.nesterov ? fadd(xi, fsub(fmul(a, P.momentum), fmul(sc.x, g))) : fadd(xi, a);
+        }
+        break;
+    case ASR_OPT_ADAGRAD: {
+        const float a = fadd(o0, fmul(g, g));
+        s0[gi] = a;
+        xn = fsub(xi, __fdiv_rn(fmul(g, sc.x), fadd(__fsqrt_rn(a), P.epsilon)));
+    } break;
+    case ASR_OPT_ADADELTA: {
+        const float rho = 0.95f, eps = 1e-7f, omr = fsub(1.0f, rho);
+        const float a = fadd(fmul(o0, rho), fmul(fmul(g, g), omr));
+        s0[gi] = a;
+        const float upd = fmul(fmul(__fsqrt_rn(fadd(o1, eps)), __fdiv_rn(1.0f, __fsqrt_rn(fadd(a, eps)))), g);
+        xn = fsub(xi, fmul(upd, sc.x));
+        s1[gi] = fadd(fmul(o1, rho), fmul(fmul(upd, upd), omr));
+    } break;
+    case ASR_OPT_ADAMAX: {
+        const float m = fadd(o0, fmul(fsub(g, o0), P.omb1));
+        s0[gi] = m;
+        const float v = fmaxf(fmul(P.beta_2, o1), fabsf(g));
+        s1[gi] = v;
+        xn = fsub(xi, fmul(sc.y, __fdiv_rn(m, fadd(v, P.epsilon))));
+    } break;
+    default: {
+        const float m = fadd(o0, fmul(fsub(g, o0), P.omb1));
+        const float v = fadd(o1, fmul(fsub(fmul(g, g), o1), P.omb2));
+        s0[gi] = m;
+        s1[gi] = v;
+        float den = v;
+        if (P.amsgrad) { den = fmaxf(o2, v); s2[gi] = den; }
+        xn = fsub(xi, __fdiv_rn(fmul(m, sc.y), fadd(__fsqrt_rn(den), P.epsilon)));
+    } break;
+    }
+    return xn;
+}
+
 #ifdef ASR_K2_TRACE   // development build only (scripts/dev/k2_trace.py): clock64 stamps of one CTA's hand-offs
 __device__ long long g_k2_trace[16][128][4];
 __device__ long long g_k2_misc[16][4];
@@ -677,52 +725,133 @@ k_gradient_update(const __grid_constant__ CUtensorMap rmap, const float* __restr
                 const size_t gi = (size_t)b * plane + i;
                 if (WRITE_GRAD) { x_next[gi] = g; continue; }
                 const float o0 = v0_[rr][c], o1 = v1_[rr][c], o2 = v2_[rr][c];
-                float xn;
-                switch (P.optimizer) {
-                case ASR_OPT_SGD:
-                    if (P.momentum == 0.0f) {
-                        xn = fsub(xi, fmul(sc.x, g));
-                    } else {
-                        const float a = fsub(fmul(o0, P.momentum), fmul(sc.x, g));
-                        s0[gi] = a;
-                        xn = P.nesterov ? fadd(xi, fsub(fmul(a, P.momentum), fmul(sc.x, g))) : fadd(xi, a);
-                    }
-                    break;
-                case ASR_OPT_ADAGRAD: {
-                    const float a = fadd(o0, fmul(g, g));
-                    s0[gi] = a;
-                    xn = fsub(xi, __fdiv_rn(fmul(g, sc.x), fadd(__fsqrt_rn(a), P.epsilon)));
-                } break;
-                case ASR_OPT_ADADELTA: {
-                    const float rho = 0.95f, eps = 1e-7f, omr = fsub(1.0f, rho);
-                    const float a = fadd(fmul(o0, rho), fmul(fmul(g, g), omr));
-                    s0[gi] = a;
-                    const float upd = fmul(fmul(__fsqrt_rn(fadd(o1, eps)), __fdiv_rn(1.0f, __fsqrt_rn(fadd(a, eps)))), g);
-                    xn = fsub(xi, fmul(upd, sc.x));
-                    s1[gi] = fadd(fmul(o1, rho), fmul(fmul(upd, upd), omr));
-                } break;
-                case ASR_OPT_ADAMAX: {
-                    const float m = fadd(o0, fmul(fsub(g, o0), P.omb1));
-                    s0[gi] = m;
-                    const float v = fmaxf(fmul(P.beta_2, o1), fabsf(g));
-                    s1[gi] = v;
-                    xn = fsub(xi, fmul(sc.y, __fdiv_rn(m, fadd(v, P.epsilon))));
-                } break;
-                default: {
-                    const float m = fadd(o0, fmul(fsub(g, o0), P.omb1));
-                    const float v = fadd(o1, fmul(fsub(fmul(g, g), o1), P.omb2));
-                    s0[gi] = m;
-                    s1[gi] = v;
-                    float den = v;
-                    if (P.amsgrad) { den = fmaxf(o2, v); s2[gi] = den; }
-                    xn = fsub(xi, __fdiv_rn(fmul(m, sc.y), fadd(__fsqrt_rn(den), P.epsilon)));
-                } break;
-                }
+                const float xn = optimizer_step(P, sc, g, xi, o0, o1, o2, gi, s0, s1, s2);
                 x_next[gi] = xn;
             }
         }
     }
     K2_TM(3);
+}
+
+// ================================================================================================
+// Any even integer output/feature ratio other than 4 (Superresolution's default feature_size (64,64) -> (512,512) is x8,
+// superresolution.py:28): the literal operator sequence, one thread per output, no tiling.  Correct for every even ratio
+// S >= 2; only the x4 shape of the reference's callers has the tuned kernels above.  Same arithmetic, bit-identical to the oracle.
+// ================================================================================================
+// bilinear_interpolation() of ImageProjectiveTransformV3 at source coordinate (ix, iy); rd(y, x) supplies the taps (zero fill inside)
+template <class Read>
+__device__ __forceinline__ float proj_bilinear(float ix, float iy, Read rd) {
+    const float fx = floorf(ix), fy = floorf(iy);
+    const float cx = fadd(fx, 1.0f), cy = fadd(fy, 1.0f);
+    const long x0 = (long)fx, y0 = (long)fy, x1 = (long)cx, y1 = (long)cy;
+    const float wx0 = fsub(cx, ix), wx1 = fsub(ix, fx), wy0 = fsub(cy, iy), wy1 = fsub(iy, fy);
+    const float top = fadd(fmul(wx0, rd(y0, x0)), fmul(wx1, rd(y0, x1)));
+    const float bot = fadd(fmul(wx0, rd(y1, x0)), fmul(wx1, rd(y1, x1)));
+    return fadd(fmul(wy0, top), fmul(wy1, bot));
+}
+
+// tf.image.resize weights of output index o (half-pixel centres)
+__device__ __forceinline__ void resize_taps(int o, float scale, int in_size, int& lo, int& hi, float& lerp) {
+    const float src = fsub(fmul(fadd((float)o, 0.5f), scale), 0.5f);
+    const float f = floorf(src);
+    lo = max((int)f, 0);
+    hi = min((int)ceilf(src), in_size - 1);
+    lerp = fsub(src, f);
+}
+
+__global__ void __launch_bounds__(128)
+kg_forward_residual(const float* __restrict__ x_cur, const float* __restrict__ copies, float* __restrict__ resid,
+                    const FwdXf* __restrict__ fwd, const int* __restrict__ src_idx, const ImgParams* __restrict__ ip, int it, int N,
+                    int h, int w, int wp, int H, int W) {
+    const int b = blockIdx.z, ks = blockIdx.y;
+    const ImgParams P = ip[b];
+    if (ks >= P.n_kept || it >= P.num_iter) return;
+    const int cell = blockIdx.x * blockDim.x + threadIdx.x;
+    if (cell >= h * w) return;
+    const int i = cell / w, j = cell - i * w;
+    const FwdXf T = fwd[(size_t)b * N + ks];
+    const float* x = x_cur + (size_t)b * H * W;
+    auto xread = [&](long y, long xx) -> float { return (y >= 0 && y < H && xx >= 0 && xx < W) ? x[y * W + xx] : 0.0f; };
+    auto p = [&](long qy, long qx) -> float {   // rotated image on the canvas, zero outside
+        if (qy < 0 || qy >= H || qx < 0 || qx >= W) return 0.0f;
+        const float X = (float)qx, Y = (float)qy;
+        return proj_bilinear(affine_coord(T.r0, X, T.r1, Y, T.r2), affine_coord(T.r3, X, T.r4, Y, T.r5), xread);
+    };
+    auto z = [&](int zy, int zx) -> float {     // translated image: (1*X + 0*Y) + t == X + t exactly
+        return proj_bilinear(fadd((float)zx, T.tx), fadd((float)zy, T.ty), p);
+    };
+    int ylo, yhi, xlo, xhi;
+    float yl, xl;
+    resize_taps(i, (float)H / (float)h, H, ylo, yhi, yl);
+    resize_taps(j, (float)W / (float)w, W, xlo, xhi, xl);
+    const float tl = z(ylo, xlo), tr = z(ylo, xhi), bl = z(yhi, xlo), br = z(yhi, xhi);
+    const float t = fadd(tl, fmul(fsub(tr, tl), xl));
+    const float bb = fadd(bl, fmul(fsub(br, bl), xl));
+    const float D = fadd(t, fmul(fsub(bb, t), yl));
+    const float yk = copies[(((size_t)P.stack * N + src_idx[(size_t)b * N + ks]) * h + i) * w + j];
+    resid[(((size_t)b * N + ks) * h + i) * wp + j] = fsub(D, yk);
+}
+
+template <bool WRITE_GRAD>
+__global__ void __launch_bounds__(128)
+kg_gradient_update(const float* __restrict__ x_cur, float* __restrict__ x_next, float* __restrict__ s0, float* __restrict__ s1,
+                   float* __restrict__ s2, const float* __restrict__ resid, const InvXf* __restrict__ inv,
+                   const ImgParams* __restrict__ ip, const Sched* __restrict__ sched, int it, int N, int h, int w, int wp, int H, int W,
+                   int B, int S) {
+    const int b = blockIdx.y;
+    const ImgParams P = ip[b];
+    if (it >= P.num_iter) return;
+    const int pix = blockIdx.x * blockDim.x + threadIdx.x;
+    if (pix >= H * W) return;
+    const int Y = pix / W, X = pix - Y * W;
+    const float Xf = (float)X, Yf = (float)Y;
+    const int c_lo = S / 2 - 1;   // the two rows/columns of each SxS block that tf.image.resize samples (weights 0.5 each)
+    float acc = 0.0f;
+    for (int k = 0; k < P.n_kept; ++k) {
+        const InvXf T = inv[(size_t)b * N + k];
+        const float* r = resid + ((size_t)b * N + k) * h * wp;
+        auto ghr = [&](long y, long xx) -> float {   // ResizeBilinearGrad(2*lambda_df*r): 0.25*g on the sampled positions, else 0
+            if (y < 0 || y >= H || xx < 0 || xx >= W) return 0.0f;
+            const int cy = (int)y / S, py = (int)y - cy * S, cx = (int)xx / S, px = (int)xx - cx * S;
+            if ((py != c_lo && py != c_lo + 1) || (px != c_lo && px != c_lo + 1)) return 0.0f;
+            return fmul(fmul(0.5f, fmul(P.two_ldf, r[cy * wp + cx])), 0.5f);
+        };
+        auto u = [&](long qy, long qx) -> float {    // warp-grad of the translate: the op with the inverted transform
+            if (qy < 0 || qy >= H || qx < 0 || qx >= W) return 0.0f;
+            return proj_bilinear(fadd((float)qx, T.ux), fadd((float)qy, T.uy), ghr);
+        };
+        acc = fadd(acc, proj_bilinear(affine_coord(T.b0, Xf, T.b1, Yf, T.b2), affine_coord(T.b3, Xf, T.b4, Yf, T.b5), u));
+    }
+    // regularisers and the optimizer step, as in k_gradient_update's epilogue
+    const size_t plane = (size_t)H * W, i = (size_t)Y * W + X, gi = (size_t)b * plane + i;
+    const float* xc = x_cur + (size_t)b * plane;
+    const float xi = xc[i];
+    float g = acc;
+    if (P.use_btv) {
+        for (int hh = -2; hh <= 2; ++hh) {
+            for (int vv = 0; vv <= 2; ++vv) {
+                const float lw = P.btv_lw[abs(hh) + vv];
+                const int xs = X - hh, ys = Y - vv, xt = X + hh, yt = Y + vv;
+                const float shifted = (xs >= 0 && xs < W && ys >= 0) ? xc[(size_t)ys * W + xs] : 0.0f;
+                const float gd = fmul(lw, sgn(fsub(xi, shifted)));
+                const float gb = (xt >= 0 && xt < W && yt < H) ? fmul(lw, sgn(fsub(xc[(size_t)yt * W + xt], xi))) : 0.0f;
+                g = fadd(g, fsub(gd, gb));
+            }
+        }
+    } else {
+        if (Y > 0) g = fadd(g, fmul(P.lambda_tv, sgn(fsub(xi, xc[i - W]))));
+        if (X > 0) g = fadd(g, fmul(P.lambda_tv, sgn(fsub(xi, xc[i - 1]))));
+        if (Y < H - 1) g = fsub(g, fmul(P.lambda_tv, sgn(fsub(xc[i + W], xi))));
+        if (X < W - 1) g = fsub(g, fmul(P.lambda_tv, sgn(fsub(xc[i + 1], xi))));
+    }
+    g = fadd(g, fmul(P.lambda_l2, fmul(xi, 2.0f)));
+    if (P.lambda_l1 > 0.0f) g = fadd(g, fmul(P.lambda_l1, sgn(xi)));
+    if (WRITE_GRAD) { x_next[gi] = g; return; }
+    const Sched sc = sched[(size_t)it * B + b];
+    const bool need0 = !(P.optimizer == ASR_OPT_SGD && P.momentum == 0.0f);
+    const bool need1 = P.optimizer == ASR_OPT_ADAM || P.optimizer == ASR_OPT_ADADELTA || P.optimizer == ASR_OPT_ADAMAX;
+    const bool need2 = P.optimizer == ASR_OPT_ADAM && P.amsgrad;
+    x_next[gi] = optimizer_step(P, sc, g, xi, need0 ? s0[gi] : 0.0f, need1 ? s1[gi] : 0.0f, need2 ? s2[gi] : 0.0f, gi, s0, s1, s2);
 }
 
 // ================================================================================================
@@ -831,8 +960,8 @@ static Layout make_layout(int B, int N, int h, int w, int H, int W, int max_iter
 
 static int check_shapes(int B, int N, int h, int w, int H, int W) {
     if (B <= 0 || N <= 0 || h <= 0 || w <= 0) return fail(ASR_EINVAL, "B, N, h, w must be positive (got %d %d %d %d)", B, N, h, w);
-    if (H != 4 * h || W != 4 * w)
-        return fail(ASR_EUNSUPPORTED, "only output_size == 4 * feature_size is implemented (got %dx%d -> %dx%d)", h, w, H, W);
+    if (H <= 0 || W <= 0 || H % h != 0 || W % w != 0 || H / h != W / w || (H / h) % 2 != 0)
+        return fail(ASR_EUNSUPPORTED, "output_size must be feature_size times an even integer (got %dx%d -> %dx%d)", h, w, H, W);
     if (B > 65535 || N > 65535) return fail(ASR_EINVAL, "B and N must be <= 65535");
     if (H > 16384 || W > 16384) return fail(ASR_EINVAL, "output larger than 16384 pixels per side (fp32 address arithmetic of the gathers)");
     if ((double)B * N * (double)(h > w ? h : w) * 16.0 >= 4294967296.0 || (double)N * h * w >= 2147483648.0)
@@ -1109,11 +1238,30 @@ static int solve_impl(const AsrSolveParams* params, int n_params, const float* d
             ASR_LAUNCH(k_fill, 64, 256, 0, st, D.s0 + (size_t)b * plane, T.hp[b].initial_accumulator_value, plane);
     ASR_LAUNCH(k_init_upsample, dim3((W + 31) / 32, (H + 7) / 8, B), dim3(32, 8), 0, st, d_copies, D.ip, D.xa, N, h, w, H, W);
 
+    const int wp = pitch4(w);
+    if (H != 4 * h) {
+        // any other even ratio (x2, x6, x8 ...): the literal one-thread-per-output kernels
+        const int S = H / h;
+        for (int it = 0; it < T.max_iter; ++it) {
+            float* xc = (it & 1) ? D.xb : D.xa;
+            float* xn = (it & 1) ? D.xa : D.xb;
+            ASR_LAUNCH_TIMED(0, kg_forward_residual, dim3((h * w + 127) / 128, T.max_kept, B), 128, 0, st, xc, d_copies, D.resid, D.fwd, D.src,
+                             D.ip, it, N, h, w, wp, H, W);
+            ASR_LAUNCH_TIMED(1, kg_gradient_update<false>, dim3((H * W + 127) / 128, B), 128, 0, st, xc, xn, D.s0, D.s1, D.s2, D.resid, D.inv,
+                             D.ip, D.sched, it, N, h, w, wp, H, W, B, S);
+        }
+        ASR_CUDA_TRY(cudaGetLastError());
+        if (d_loss_out) {
+            if (int e = launch_loss(D, n_params, d_loss_out, B, N, h, w, H, W, st)) return e;
+        }
+        ASR_LAUNCH(k_select_output, dim3(32, B), 256, 0, st, D.xa, D.xb, D.ip, d_x_out, plane);
+        ASR_CUDA_TRY(cudaGetLastError());
+        return ASR_OK;
+    }
     const int ntj = k1_tiles_x(w), nti = k1_tiles_y(h);
     const int t1 = ntj * nti;
     CUtensorMap map_a, map_b, map_r;
     const int box_rows = T.small_box ? K1_XR_SMALL : K1_XR_BIG;
-    const int wp = pitch4(w);
     if (int e = make_x_map(&map_a, D.xa, B, H, W, box_rows)) return e;
     if (int e = make_x_map(&map_b, D.xb, B, H, W, box_rows)) return e;
     if (int e = make_r_map(&map_r, D.resid, B * N, h, w)) return e;
@@ -1210,10 +1358,16 @@ extern "C" int asr_loss_grad_batched(const AsrSolveParams* params, int n_params,
 
     const size_t plane = (size_t)H * W;
     ASR_CUDA_TRY(cudaMemcpyAsync(D.xa, d_x, sizeof(float) * B * plane, cudaMemcpyDeviceToDevice, st));
+    const int wp = pitch4(w);
+    if (H != 4 * h) {
+        ASR_LAUNCH_TIMED(0, kg_forward_residual, dim3((h * w + 127) / 128, T.max_kept, B), 128, 0, st, D.xa, d_copies, D.resid, D.fwd, D.src,
+                         D.ip, 0, N, h, w, wp, H, W);
+        ASR_LAUNCH_TIMED(1, kg_gradient_update<true>, dim3((H * W + 127) / 128, B), 128, 0, st, D.xa, D.xb, D.s0, D.s1, D.s2, D.resid, D.inv,
+                         D.ip, D.sched, 0, N, h, w, wp, H, W, B, H / h);
+    } else {
     const int ntj = k1_tiles_x(w), nti = k1_tiles_y(h);
     const int t1 = ntj * nti;
     CUtensorMap map_a, map_r;
-    const int wp = pitch4(w);
     const int box_rows = T.small_box ? K1_XR_SMALL : K1_XR_BIG;
     if (int e = make_x_map(&map_a, D.xa, B, H, W, box_rows)) return e;
     if (int e = make_r_map(&map_r, D.resid, B * N, h, w)) return e;
@@ -1224,6 +1378,7 @@ extern "C" int asr_loss_grad_batched(const AsrSolveParams* params, int n_params,
                   div_magic(ntj), 0);
     ASR_LAUNCH_K2(true, T.any_btv, k2_tile_height(B, H, W), H, W, B, st, map_r, D.xa, D.xb, D.s0, D.s1, D.s2, D.tapc, D.tapr, D.inv, D.ip,
                   D.sched, 0, N, h, w, H, W, B, 0);
+    }
     ASR_CUDA_TRY(cudaGetLastError());
     if (d_grad) ASR_CUDA_TRY(cudaMemcpyAsync(d_grad, D.xb, sizeof(float) * B * plane, cudaMemcpyDeviceToDevice, st));
     if (d_resid) {

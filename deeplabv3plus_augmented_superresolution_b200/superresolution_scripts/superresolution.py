@@ -89,8 +89,8 @@ class Superresolution:
 
     def _check_sizes(self, h, w):
         H, W = self.output_size
-        if (H, W) != (4 * h, 4 * w):
-            raise NotImplementedError(f"libasr implements output_size == 4 * feature map size; got {(h, w)} -> {(H, W)}")
+        if H % h or W % w or H // h != W // w or (H // h) % 2:
+            raise NotImplementedError(f"libasr implements output_size == feature map size times an even integer; got {(h, w)} -> {(H, W)}")
 
     # ---- reference API ---------------------------------------------------------------------------------------
     def augmented_superresolution(self, augmented_copies, angles, shifts):
@@ -102,7 +102,7 @@ class Superresolution:
         keep = self._dropout_keep(n)
         params = self._solve_params(self.optimizer.iterations)
         x, loss = _lib.solve_batched(stack[None], np.asarray(angles, np.float32)[None], np.asarray(shifts, np.float32)[None],
-                                     params, keep=None if keep is None else keep[None], want_loss=True)
+                                     params, keep=None if keep is None else keep[None], want_loss=True, output_size=self.output_size)
         self.optimizer.iterations += int(self.num_iter)     # Keras' shared step counter keeps counting
         out = x[0].cpu().numpy()[..., None]
         loss = float(loss[0].item())
@@ -138,7 +138,7 @@ class Superresolution:
             params_list = [self._solve_params(base + j * int(self.num_iter)) for j in range(B)]
             if advance_iterations:
                 self.optimizer.iterations += B * int(self.num_iter)
-        return _lib.solve_batched(copies, angles, shifts, params_list, keep=keep, want_loss=want_loss)
+        return _lib.solve_batched(copies, angles, shifts, params_list, keep=keep, want_loss=want_loss, output_size=self.output_size)
 
     def backproject_batched(self, copies, angles, shifts, mode):
         torch = _lib._torch()

@@ -96,7 +96,8 @@ int asr_l2_read_probe(const void* d_buf, size_t bytes, int passes, void* d_sink,
  *   h_keep      NULL, or [B,N] bytes: 0 drops the copy (copy dropout, superresolution.py:47-53)
  *   d_x_out     [B,H,W] solved high-resolution maps
  *   d_loss_out  NULL or [B]: loss of the last iteration before its update (superresolution.py:137)
- * Supported: H == 4h, W == 4w (every caller in the reference), W % 4 == 0.                      */
+ * Supported: H == S*h, W == S*w for an even integer S; S == 4 (every caller in the reference) runs the tuned kernels,
+ * any other even S (x2, x6, x8: Superresolution's default feature_size is 64x64 -> 512x512) the literal per-output kernels. */
 int asr_solve_workspace_bytes(int B, int N, int h, int w, int H, int W, int max_iter, size_t* bytes);
 int asr_solve_batched(const AsrSolveParams* params, int n_params,
                       const float* d_copies, const float* h_angles, const float* h_shifts,

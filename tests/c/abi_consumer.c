@@ -12,7 +12,7 @@ int main(void) {
     memset(&p, 0, sizeof p);
     if (asr_version() != ASR_VERSION) { printf("version %d\n", asr_version()); return 1; }
     if (asr_solve_workspace_bytes(2, 100, 128, 128, 512, 512, 300, &need) != ASR_OK || need == 0) return 2;
-    if (asr_solve_workspace_bytes(1, 4, 64, 64, 512, 512, 10, &need) != ASR_EUNSUPPORTED) return 3;
+    if (asr_solve_workspace_bytes(1, 4, 64, 64, 192, 192, 10, &need) != ASR_EUNSUPPORTED) return 3;   /* odd ratio */
     if (strstr(asr_last_error(), "feature_size") == NULL) return 4;
     if (asr_solve_workspace_bytes(2, 100, 128, 128, 512, 512, 300, NULL) != ASR_ENULL) return 5;
     /* null pointers are rejected before any CUDA call */

@@ -44,8 +44,10 @@ def test_workspace_query_and_error_codes(L):
     lo = 2 * (5 * 512 * 512 * 4 + 100 * 128 * 128 * 4)
     assert lo <= need.value <= lo + (1 << 22)
     assert L.asr_solve_workspace_bytes(2, 100, 128, 128, 512, 512, 300, None) == -2
-    assert L.asr_solve_workspace_bytes(1, 4, 64, 64, 512, 512, 10, C.byref(need)) == -3     # scale 8 not implemented
-    assert b"4 * feature_size" in L.asr_last_error()
+    assert L.asr_solve_workspace_bytes(1, 4, 64, 64, 512, 512, 10, C.byref(need)) == 0      # x8: Superresolution's default feature_size
+    assert L.asr_solve_workspace_bytes(1, 4, 64, 64, 192, 192, 10, C.byref(need)) == -3     # odd ratio
+    assert b"even integer" in L.asr_last_error()
+    assert L.asr_solve_workspace_bytes(1, 4, 64, 64, 512, 256, 10, C.byref(need)) == -3     # anisotropic
     assert L.asr_solve_workspace_bytes(0, 4, 16, 16, 64, 64, 10, C.byref(need)) == -1
 
     p = _lib.SolveParams(num_iter=3).to_c()
@@ -55,7 +57,7 @@ def test_workspace_query_and_error_codes(L):
                                                         None, B, 4, h, h, H, H, fake, None, fake, ws, None)
     assert L.asr_solve_batched(*args(p, 1, ws=16)) == -5                                     # workspace too small
     assert L.asr_solve_batched(*args(p, 2)) == -1                                           # n_params must be 1 or B
-    assert L.asr_solve_batched(*args(p, 1, H=128)) == -3
+    assert L.asr_solve_batched(*args(p, 1, H=48)) == -3
     pb = _lib.SolveParams(optimizer="adam").to_c(); pb.optimizer = 9
     assert L.asr_solve_batched(*args(pb, 1)) == -1 and b"optimizer" in L.asr_last_error()
     assert L.asr_solve_batched(None, 1, fake, ang.ctypes.data_as(_lib._fp), shf.ctypes.data_as(_lib._fp), None,

@@ -555,3 +555,48 @@ def test_workspace_forms_of_aux_calls():
     torch.cuda.synchronize()
     assert torch.equal(b1, b2)
     assert L.asr_backproject_batched_ws(1, copies.data_ptr(), a32.ctypes.data_as(fp), s32.ctypes.data_as(fp), 2, 5, 16, 16, 64, 64, b1.data_ptr(), ws.data_ptr(), 8, None) == -5
+
+
+# --------------------------------------------------------------------------------------------------
+# output/feature ratios other than 4 (Superresolution's default feature_size (64,64) -> (512,512) is x8)
+# --------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("case", [
+    dict(hw=(16, 16), S=8, N=5, iters=6, angle_max=0.15, shift_max=20, seed=51),
+    dict(hw=(24, 20), S=2, N=4, iters=8, angle_max=0.6, shift_max=6, seed=52, value=8.0),
+    dict(hw=(12, 16), S=6, N=3, iters=5, angle_max=2.0, shift_max=15, seed=53, kw=dict(optimizer="sgd", momentum=0.9, learning_rate=1e-4)),
+    dict(hw=(16, 16), S=8, N=4, iters=5, angle_max=0.3, shift_max=10, seed=54, kw=dict(use_btv=True, lambda_l1=0.02)),
+], ids=lambda c: f"x{c['S']}-{c['hw'][0]}x{c['hw'][1]}")
+def test_solve_other_even_ratios(case):
+    from deeplabv3plus_augmented_superresolution_b200.synthetic import make_augmented_copies
+    h, w = case["hw"]; S = case["S"]; H, W = S * h, S * w
+    kw = case.get("kw", {})
+    copies, ang, sh = make_augmented_copies(2, case["N"], (h, w), (H, W), case["angle_max"], case["shift_max"], seed=case["seed"],
+                                            value=case.get("value", 1.0), device="cuda")
+    x, loss = A.solve_batched(copies, ang, sh, A.SolveParams(num_iter=case["iters"], **kw), want_loss=True, output_size=(H, W))
+    cp = copies.cpu().numpy()
+    for b in range(2):
+        xo, lo = O.augmented_superresolution(cp[b], ang[b], sh[b], O.SolveParams(num_iter=case["iters"], **kw), output_size=(H, W))
+        assert np.array_equal(x[b].cpu().numpy(), xo[..., 0]), np.abs(x[b].cpu().numpy() - xo[..., 0]).max()
+        assert_loss_close(float(loss[b]), lo)
+    # single evaluation: residual and gradient
+    xs = torch.rand((2, H, W), device="cuda")
+    resid, grad, _ = A.loss_grad_batched(xs, copies, ang, sh, A.SolveParams(**kw))
+    for b in range(2):
+        _, g, r = O.loss_and_grad(xs[b].cpu().numpy(), cp[b], ang[b], sh[b], O.SolveParams(**kw), want_resid=True)
+        np.testing.assert_array_equal(resid[b].cpu().numpy(), r)
+        np.testing.assert_array_equal(grad[b].cpu().numpy(), g)
+
+
+def test_reference_class_default_feature_size_is_x8():
+    """Superresolution() without feature_size (64,64 -> 512,512: superresolution.py:28) goes through the reference-named call."""
+    from deeplabv3plus_augmented_superresolution_b200.superresolution_scripts.optimizer import Optimizer
+    from deeplabv3plus_augmented_superresolution_b200.superresolution_scripts.superresolution import Superresolution
+    from deeplabv3plus_augmented_superresolution_b200.synthetic import make_augmented_copies
+    copies, ang, sh = make_augmented_copies(1, 4, (64, 64), (512, 512), 0.15, 40, seed=61)
+    sr = Superresolution(1.0, 0.3, 0.7, 0.0, num_iter=3, num_aug=4, optimizer=Optimizer(amsgrad=True, lr_scheduler=True, decay_steps=60, decay_rate=0.3))
+    assert sr.feature_size == (64, 64) and sr.output_size == (512, 512)
+    x, loss = sr.augmented_superresolution([c[..., None] for c in copies[0].numpy()], ang[0], sh[0])
+    xo, lo = O.augmented_superresolution(copies[0].numpy(), ang[0], sh[0], O.SolveParams(num_iter=3), output_size=(512, 512))
+    np.testing.assert_array_equal(x, xo)
+    with pytest.raises(NotImplementedError):
+        Superresolution(1.0, 0.3, 0.7, 0.0, optimizer=Optimizer(), output_size=(96, 96))._check_sizes(32, 32)       # x3: odd ratio
