@@ -81,8 +81,9 @@ def test_optimizer_and_params_mapping():
     assert abs(c.lambda_tv - 0.3) < 1e-7 and abs(c.decay_rate - 0.3) < 1e-7 and c.decay_steps == 60.0
     with pytest.raises(Exception, match="must provide an instance of the Optimizer"):
         Superresolution(1, 1, 1, 0)._check_optimizer()
+    Superresolution(1, 1, 1, 0, optimizer=o, output_size=(512, 512))._check_sizes(64, 64)       # the (64,64) default: x8 is supported
     with pytest.raises(NotImplementedError):
-        Superresolution(1, 1, 1, 0, optimizer=o, output_size=(512, 512))._check_sizes(64, 64)   # the (64,64) default
+        Superresolution(1, 1, 1, 0, optimizer=o, output_size=(512, 512))._check_sizes(100, 100)   # non-integer ratio
 
 
 def test_copy_dropout_mask_is_frozen_like_a_traced_function():
