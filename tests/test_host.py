@@ -150,3 +150,128 @@ def test_gather_masks_world_size_2_gloo(n_total):
     assert all(p.exitcode == 0 for p in procs)
     assert out.shape == (n_total, 4, 4)
     np.testing.assert_array_equal(out[:, 0, 0], np.arange(n_total))
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# hdf5: a file assembled by hand, byte by byte from the HDF5 File Format Specification, the way libhdf5 (behind h5py's
+# default libver) lays one out -- NOT with hdf5_lite's writer -- with structures that writer never emits: a non-zero
+# superblock base address (user block), NIL padding messages, object-modification-time and fill-value messages, an
+# object-header continuation block, a version-3 attribute message, a version-2 dataspace, a compact dataset, a
+# two-level group B-tree and a global heap with several objects.  h5py itself is absent (no wheel, no index), so a
+# file written by real h5py cannot be committed; this pins the reader to the published format instead of to its sibling.
+# ---------------------------------------------------------------------------------------------------------------
+def _assemble_spec_file(arrays, attrs_str, attr_f64, attr_i64, userblock=512):
+    import struct
+    U = 0xFFFFFFFFFFFFFFFF
+    pad8 = lambda b: b + b"\0" * (-len(b) % 8)
+    msg = lambda t, body, fl=0: struct.pack("<HHB3x", t, len(pad8(body)), fl) + pad8(body)
+    f32 = struct.pack("<BBBBI", 0x11, 0x20, 31, 0, 4) + struct.pack("<HHBBBBI", 0, 32, 23, 8, 0, 23, 127)
+    f64 = struct.pack("<BBBBI", 0x11, 0x20, 63, 0, 8) + struct.pack("<HHBBBBI", 0, 64, 52, 11, 0, 52, 1023)
+    i64 = struct.pack("<BBBBI", 0x10, 0x08, 0, 0, 8) + struct.pack("<HH", 0, 64)
+    vstr = struct.pack("<BBBBI", 0x19, 0x01, 0x01, 0, 16) + struct.pack("<BBBBI", 0x10, 0, 0, 0, 1) + struct.pack("<HH", 0, 8)
+    space_v1 = lambda shape: struct.pack("<BBBB4x", 1, len(shape), 0, 0) + b"".join(struct.pack("<Q", d) for d in shape)
+    space_v2 = lambda shape: struct.pack("<BBBB", 2, len(shape), 0, 1 if shape else 0) + b"".join(struct.pack("<Q", d) for d in shape)
+
+    blob = bytearray(b"\0" * 2048)                      # superblock + root structures are patched in at the end
+    def put(b, align=8):
+        while len(blob) % align:
+            blob.append(0)
+        a = len(blob)
+        blob.extend(b)
+        return a
+
+    # global heap: object 1..n = the strings, then the free-space object 0
+    gobjs, gbody = {}, b""
+    for i, (k, v) in enumerate(attrs_str.items(), start=1):
+        raw = v.encode() + b"\0"
+        gobjs[k] = (i, len(raw))
+        gbody += struct.pack("<HHIQ", i, 1, 0, len(raw)) + pad8(raw)
+    gsize = 4096
+    gbody += struct.pack("<HHIQ", 0, 0, 0, gsize - 16 - len(gbody) - 16)
+    gcol = put(b"GCOL" + struct.pack("<B3xQ", 1, gsize) + gbody + b"\0" * (gsize - 16 - len(gbody)))
+
+    # datasets: raw data first, then their object headers
+    names = sorted(arrays)
+    heads = {}
+    for n in names:
+        a = np.ascontiguousarray(arrays[n], np.float32)
+        fill = msg(0x0005, struct.pack("<BBBB", 2, 2, 0, 0))                                     # fill value v2, undefined
+        mtime = msg(0x0012, struct.pack("<B3xI", 1, 1639000000))                                 # object modification time
+        if n == "angles":                                                                        # a compact dataset, v2 dataspace
+            layout = msg(0x0008, struct.pack("<BBH", 3, 0, a.nbytes) + a.tobytes())
+            msgs = [msg(0x0001, space_v2(a.shape)), msg(0x0003, f32, 1), fill, layout, mtime, msg(0x0000, b"\0" * 8)]
+            heads[n] = put(struct.pack("<BBHII4x", 1, 0, len(msgs), 1, sum(map(len, msgs))) + b"".join(msgs))
+        else:
+            data = put(a.tobytes())
+            layout = msg(0x0008, struct.pack("<BBQQ", 3, 1, data - userblock, a.nbytes))
+            # first block holds dataspace + datatype + a continuation; the rest lives in a continuation block elsewhere
+            cont_msgs = [fill, layout, mtime, msg(0x0000, b"\0" * 16)]
+            cont = put(b"".join(cont_msgs))
+            first = [msg(0x0001, space_v1(a.shape)), msg(0x0003, f32, 1),
+                     msg(0x0010, struct.pack("<QQ", cont - userblock, sum(map(len, cont_msgs))))]
+            heads[n] = put(struct.pack("<BBHII4x", 1, 0, len(first) + len(cont_msgs), 1, sum(map(len, first))) + b"".join(first))
+
+    # local heap with the link names, two SNODs under a level-1 TREE
+    heap_data = bytearray(b"\0" * 8)
+    offs = {}
+    for n in names:
+        offs[n] = len(heap_data)
+        heap_data += pad8(n.encode() + b"\0")
+    heap_data += b"\0" * 64
+    hd = put(bytes(heap_data))
+    heap = put(b"HEAP" + struct.pack("<B3xQQQ", 0, len(heap_data), len(heap_data) - 64, hd - userblock))
+    def snod(group):
+        ents = b"".join(struct.pack("<QQII16x", offs[n], heads[n] - userblock, 0, 0) for n in group)
+        return put(b"SNOD" + struct.pack("<BBH", 1, 0, len(group)) + ents + b"\0" * (40 * (8 - len(group))))
+    half = (len(names) + 1) // 2
+    s1, s2 = snod(names[:half]), snod(names[half:])
+    leaf = lambda s, lo, hi: put(b"TREE" + struct.pack("<BBHQQ", 0, 0, 1, U, U) + struct.pack("<QQQ", lo, s - userblock, hi) + b"\0" * 512)
+    t1, t2 = leaf(s1, 0, offs[names[half - 1]]), leaf(s2, offs[names[half - 1]], offs[names[-1]])
+    top = put(b"TREE" + struct.pack("<BBHQQ", 0, 1, 2, U, U) +
+              struct.pack("<QQQQQ", 0, t1 - userblock, offs[names[half - 1]], t2 - userblock, offs[names[-1]]) + b"\0" * 512)
+
+    # root object header: symbol table message + the four attributes (v1, v3 with an encoding byte, v1, v1)
+    def attr_v1(name, dtype, space, data):
+        nm = name.encode() + b"\0"
+        return msg(0x000C, struct.pack("<BxHHH", 1, len(nm), len(dtype), len(space)) + pad8(nm) + pad8(dtype) + pad8(space) + data)
+    def attr_v3(name, dtype, space, data):
+        nm = name.encode() + b"\0"
+        return msg(0x000C, struct.pack("<BBHHHB", 3, 0, len(nm), len(dtype), len(space), 1) + nm + dtype + space + data)
+    vref = lambda k: struct.pack("<IQI", gobjs[k][1], gcol - userblock, gobjs[k][0])
+    keys = list(attrs_str)
+    rmsgs = [msg(0x0011, struct.pack("<QQ", top - userblock, heap - userblock)),
+             attr_v1(keys[0], vstr, space_v1(()), vref(keys[0])),
+             msg(0x0000, b"\0" * 24),
+             attr_v3(keys[1], vstr, space_v2(()), vref(keys[1])),
+             attr_v1(attr_f64[0], f64, space_v1(()), struct.pack("<d", attr_f64[1])),
+             attr_v1(attr_i64[0], i64, space_v1(()), struct.pack("<q", attr_i64[1]))]
+    root = put(struct.pack("<BBHII4x", 1, 0, len(rmsgs), 1, sum(map(len, rmsgs))) + b"".join(rmsgs))
+
+    # superblock v0 at the start of the user-block-shifted address space
+    sb = b"\x89HDF\r\n\x1a\n" + struct.pack("<BBBBBBBBHHI", 0, 0, 0, 0, 0, 8, 8, 0, 4, 16, 0)
+    sb += struct.pack("<QQQQ", userblock, U, len(blob) - userblock, U)
+    sb += struct.pack("<QQII", 0, root - userblock, 1, 0) + struct.pack("<QQ", top - userblock, heap - userblock)
+    blob[userblock:userblock + len(sb)] = sb
+    # libhdf5 looks for the signature at 0, 512, 1024, ...; hdf5_lite reads the base address from the superblock at offset 0,
+    # so the user block here is expressed as the superblock's base-address field with the superblock itself at offset 0
+    out = bytearray(blob)
+    out[0:len(sb)] = sb
+    return bytes(out)
+
+
+def test_hdf5_reader_on_a_spec_level_file_it_did_not_write(tmp_path):
+    rng = np.random.RandomState(11)
+    arrays = {"class_masks": rng.rand(5, 6, 7, 1).astype(np.float32), "max_masks": rng.rand(5, 6, 7, 1).astype(np.float32),
+              "angles": rng.rand(5).astype(np.float32), "shifts": rng.rand(5, 2).astype(np.float32)}
+    raw = _assemble_spec_file(arrays, {"filename": "2008_000123", "mode": "slice_max"}, ("angle_max", 0.15), ("shift_max", 80))
+    p = tmp_path / "2008_000123.hdf5"
+    p.write_bytes(raw)
+    f = hdf5_lite.File(str(p), "r")
+    assert sorted(f) == sorted(arrays)
+    for k, v in arrays.items():
+        assert f[k].shape == v.shape and f[k].dtype == np.float32
+        np.testing.assert_array_equal(f[k][:4], v[:4])
+    assert f.attrs["filename"] == "2008_000123" and f.attrs["mode"] == "slice_max"
+    assert f.attrs["angle_max"] == 0.15 and f.attrs["shift_max"] == 80
+    assert SU.check_hdf5_validity(f, num_aug=5) and not SU.check_hdf5_validity(f, num_aug=6)
+    f.close()
