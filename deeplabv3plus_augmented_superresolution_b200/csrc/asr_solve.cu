@@ -6,10 +6,11 @@
 //   tape.gradient (:126-133): ResizeBilinearGrad -> warp-grad(translate) -> warp-grad(rotate) -> sum over copies
 //   optimizer.apply_gradients (:134-135, optimizer.py:21-41)
 // with two kernels per iteration for a whole batch of images:
-//   k_forward_residual   r_k = D T_k R_k x - y_k              (one CTA per 16x12 LR tile per copy, TMA-staged x box)
+//   k_forward_residual   r_k = D T_k R_k x - y_k              (one CTA per 16x16 LR tile per copy, TMA-staged x box)
 //   k_gradient_update    x' = opt(x, sum_k W_k^grad r_k + reg) (one CTA per 64x64 HR tile loops over the copies:
 //                                                               8 gather warps + 4 TMA-fed fill warps)
-// plus k_tap_tables once per solve.  The gathers run on packed fp32 (FADD2/FMUL2, two pixels per instruction).
+// plus k_tap_tables and k_forward_tables once per solve.  The gathers run on packed fp32 (FADD2/FMUL2/FFMA2, two pixels
+// per instruction).  Output/feature ratios other than 4 take the literal kg_* kernels further down.
 // Both are gather-form (no atomics) and bit-reproduce the un-fused fp32 evaluation order of the
 // TensorFlow ops (see asr_common.cuh).  DESIGN.md derives the restructurings used here and why
 // each is bit-identical to the literal two-pass evaluation.
@@ -77,9 +78,9 @@ __global__ void k_init_upsample(const float* __restrict__ copies, const ImgParam
 // For copy k and LR cell (i,j):  r = resize(translate(rotate(x)))[i,j] - y_k[i,j].
 // The resize reads only z at rows {4i+1,4i+2} x cols {4j+1,4j+2}; each z is a 2x2 stencil of the
 // rotated image p on integer positions, so one cell needs p on a 3x3 patch whose origin is
-// (4j+1+floor(-dx), 4i+1+floor(-dy)).  A CTA (16x12 cells, one copy) pulls the x region those patches can
+// (4j+1+floor(-dx), 4i+1+floor(-dy)).  A CTA (16x16 cells, one copy) pulls the x region those patches can
 // touch into shared memory with ONE TMA tensor load (cp.async.bulk.tensor; out-of-image elements arrive as
-// zeros, which is exactly the op's fill), evaluates the 48x36 needed p values with the op's arithmetic, and
+// zeros, which is exactly the op's fill), evaluates the 48x48 needed p values with the op's arithmetic, and
 // a second phase combines them per cell with per-column/row tap tables that carry the literal translate
 // weights, the zero fill of p outside the canvas, and the rounding case floor(fl(Z-dx)) == Z+floor(-dx)+1.
 // Everything that depends on the transforms only -- the box origin of every (tile, copy) and the tap tables of
@@ -92,7 +93,7 @@ constexpr int K1_TI = 16;              // ... 16 cells tall = 256 cells, one per
                                        // with 11 x 12 = 132 rows; 16 rows = 6 packed pairs per thread and no ragged tile: K1 23.9 -> see DESIGN.md)
 constexpr int K1_THREADS = 256;
 constexpr int K1_GATHER = 192;         // threads of the gather phase: 48 p-columns x 4 row groups of 12 rows
-constexpr int K1_PC = 3 * K1_TJ;       // needed p columns (48) and rows (36) per tile
+constexpr int K1_PC = 3 * K1_TJ;       // needed p columns (48) and rows (48) per tile
 constexpr int K1_PR = 3 * K1_TI;
 constexpr int K1_PBS = K1_PC;          // p buffer stride 48: 3 rows = 144 = 16 (mod 32) floats, so the two cell rows a warp reads in
                                        // the second phase land on complementary bank sets (stride 49 collided on one bank: 2 wavefronts per load)
