@@ -312,20 +312,30 @@ constexpr int K2_GW = ASR_K2_GW;       // gather warps; thread owns pixels (lane
 // fill warps: 4 in the throughput variant (64-row tiles, two CTAs per SM); 8 in the latency variant (32-row tiles, one lone CTA per
 // SM, where the fill warps' serial latency per copy is what the gather warps wait for)
 #ifndef ASR_K2_FW64
-#define ASR_K2_FW64 4
+#define ASR_K2_FW64 8
 #endif
 #ifndef ASR_K2_AHEAD
-#define ASR_K2_AHEAD 2
+#define ASR_K2_AHEAD 3
 #endif
-template <int TY> struct K2Fill { static constexpr int warps = TY == 64 ? ASR_K2_FW64 : 8, threads = 32 * (K2_GW + warps), ctas = TY == 64 ? 2 : 1; };
-// -DASR_K2_FW64=8 builds the throughput variant with 8 fill warps and a register split between the roles (setmaxnreg, per
-// warpgroup of 4 warps): with 16 warps and two CTAs per SM the launch gives every thread 64 registers; the fill warpgroups hand
-// theirs back down to 40 and the gather warpgroups grow to 88, the budget their 16 accumulators + 8-deep unrolled gather needs
-// (8*88 + 8*40 = 16*64).  Measured (r02e): bit-exact, no spills, same speed as 4 fill warps (30.18 vs 30.14 us) -- the copy loop
-// is issue-bound, the fill warps are starved of issue slots rather than short of warps -- so 4 stays the default.
+#ifndef ASR_K2_PRODUCER
+#define ASR_K2_PRODUCER 1
+#endif
+// non-gather warps of a CTA.  With 8 of them the last one is a PRODUCER: it only issues the async staging copies (the clock64
+// trace showed the issuing thread's ~800 clk per copy sitting on the fill's critical path when a fill warp did it), the other
+// seven fill.
+template <int TY> struct K2Fill {
+    static constexpr int warps = TY == 64 ? ASR_K2_FW64 : 8, threads = 32 * (K2_GW + warps), ctas = TY == 64 ? 2 : 1;
+    static constexpr bool producer = ASR_K2_PRODUCER && warps == 8;
+    static constexpr int fillers = producer ? warps - 1 : warps;
+};
+// The throughput variant (64-row tiles, two CTAs per SM) runs 8 gather warps + 7 fill warps + 1 producer warp with a register split
+// between the roles (setmaxnreg, per warpgroup of 4 warps): with 16 warps and two CTAs per SM the launch gives every thread 64
+// registers; the fill/producer warpgroups hand theirs back down to 40 and the gather warpgroups grow to 88, the budget their 16
+// accumulators + 8-deep unrolled gather needs (8*88 + 8*40 = 16*64).  Measured (r02, us per image-iteration at 250 images):
+// 4 fill warps, staging 2 ahead 29.2; 8 fill warps 30.2 (no gain by itself: the loop is issue-bound); 7 fill + producer,
+// staging 3 ahead 28.4.  -DASR_K2_FW64=4 -DASR_K2_AHEAD=2 rebuilds the 12-warp variant.
 constexpr bool K2_REG_SPLIT = (ASR_K2_FW64 == 8) && (K2_GW == 8);
-constexpr int K2_AHEAD = ASR_K2_AHEAD;   // copies the async staging (residual box + tap rows) runs ahead of the fill: the residuals of a big batch
-                                         // come from DRAM, two copies (~4000 clk) of lead left the fill waiting 320 clk per copy (clock64 trace)
+constexpr int K2_AHEAD = ASR_K2_AHEAD;   // copies the async staging (residual box + tap rows) runs ahead of the fill (at most K2_STAGES - 1)
 constexpr int K2_NG = 32 * K2_GW;
 constexpr int K2_US = 96;              // u tile stride: 64*sqrt(2)+2+3 < 96, multiple of 32
 template <int TY> struct K2Rows { static constexpr int value = TY == 64 ? 96 : 80; };   // u tile rows: sqrt(63^2+(TY-1)^2)+2 -> cells
@@ -487,7 +497,7 @@ k_gradient_update(const __grid_constant__ CUtensorMap rmap, const float* __restr
     if (tid == 0) {
 #pragma unroll
         for (int i = 0; i < K2_STAGES; ++i) mbar_init(&stage_bar[i], 3);   // three async copies per stage
-        mbar_init(&full_bar[0], K2_FW); mbar_init(&full_bar[1], K2_FW);   // one arrival per fill warp
+        mbar_init(&full_bar[0], K2Fill<TY>::fillers); mbar_init(&full_bar[1], K2Fill<TY>::fillers);   // one arrival per fill warp
     }
     const bool gather_role = warp < K2_GW;
 
@@ -510,7 +520,9 @@ k_gradient_update(const __grid_constant__ CUtensorMap rmap, const float* __restr
             // cells wide).  Everything the fill reads was staged by async copies issued two copies earlier by one
             // thread: no address arithmetic, bounds tests or table building is left in these warps.
             const int fw = warp - K2_GW;
-            constexpr int ROWS = (K2_UR / 4 + K2_FW - 1) / K2_FW;   // cell rows per fill warp
+            constexpr int K2_FILLERS = K2Fill<TY>::fillers;
+            constexpr int ROWS = (K2_UR / 4 + K2_FILLERS - 1) / K2_FILLERS;   // cell rows per fill warp
+            const bool is_producer = K2Fill<TY>::producer && fw == K2_FW - 1;
             const size_t slot0 = (size_t)(b_base + b) * N + k0;
             const int ncw = w + 2 * K2_TPAD, nrw = h + 2 * K2_TPAD;
             auto stage_copy = [&](int kq) {   // one thread: residual box + tap rows of copy kq -> stage (k0+kq) % 4
@@ -521,7 +533,7 @@ k_gradient_update(const __grid_constant__ CUtensorMap rmap, const float* __restr
                 bulk_load(&S->ctap[0][0], tapc + ((slot0 + kq) * ncw + bq.cbx0 + K2_TPAD) * 4, K2_TAP_BYTES, bar);
                 bulk_load(&S->rtap[0][0], tapr + ((slot0 + kq) * nrw + bq.cby0 + K2_TPAD) * 4, K2_TAP_BYTES, bar);
             };
-            const bool issuer = (fw == 0 && lane == 0);
+            const bool issuer = lane == 0 && (K2Fill<TY>::producer ? is_producer : fw == 0);
             int next_q = 0;   // issuer only: first copy of the chunk whose staging has not been issued yet
             if (issuer) for (; next_q < K2_AHEAD && next_q < nc; ++next_q) stage_copy(next_q);
             for (int kc = 0; kc < nc; ++kc) {
@@ -538,6 +550,7 @@ k_gradient_update(const __grid_constant__ CUtensorMap rmap, const float* __restr
                 if (issuer)
                     while (next_q <= kc + K2_AHEAD && next_q < nc && (next_q < K2_STAGES || (kc >= 2 && next_q - K2_STAGES <= kc - 1)))
                         stage_copy(next_q++);
+                if (is_producer) continue;   // the producer warp neither fills nor arrives on "full"
                 mbar_wait(&stage_bar[gk & (K2_STAGES - 1)], (gk / K2_STAGES) & 1);
                 K2_TR(2);
                 if (live && lane < ncx) {
@@ -547,7 +560,7 @@ k_gradient_update(const __grid_constant__ CUtensorMap rmap, const float* __restr
                     float4* ucol = reinterpret_cast<float4*>(ut + ub * (K2_US * K2_UR)) + lane;
     #pragma unroll
                     for (int j = 0; j < ROWS; ++j) {
-                        const int cyi = fw + K2_FW * j;
+                        const int cyi = fw + K2_FILLERS * j;
                         if (cyi < ncy) {
                             const float g = fmul(0.25f, fmul(P.two_ldf, S->r[cyi][xo]));   // g_hr on the cell's 2x2 positions
                             const float t0 = fmul(ca.y, g);                           // phase 0: taps (0, g)
