@@ -287,8 +287,9 @@ k_forward_residual(const __grid_constant__ CUtensorMap xmap, const float* __rest
 // TensorFlow's gradient of the data term for copy k at HR pixel X is
 //     v_k(X) = bilinear(u_k, Rinv_k X),   u_k(q) = bilinear(g_hr, q + d_k),
 //     g_hr = ResizeBilinearGrad(2*lambda_df*r_k) = 0.25*g on the four positions {4i+1,4i+2}x{4j+1,4j+2}.
-// The CTA owns a 64x64 HR tile and loops over the copies with two kinds of warps:
-//   * 4 fill warps materialise u_k on the bounding box of Rinv_k(tile) in shared memory, one LR cell ->
+// The CTA owns a 64x64 HR tile and loops over the copies with three kinds of warps:
+//   * 1 producer warp issues the async staging copies (residual box by TMA, tap-table rows by bulk copies) three copies ahead;
+//   * 7 fill warps materialise u_k on the bounding box of Rinv_k(tile) in shared memory, one LR cell ->
 //     the 4x4 block of q positions that cell feeds (q+floor(d) in [4c,4c+3]); the block's values follow
 //     the literal 2-tap sums, which collapse to w_b*g / (w_a*g + w_b*g) / w_a*g / 0 by phase because the
 //     other tap reads an exact zero.  Phase 3 is a whole zero row/column of the tile: those rows are zeroed
@@ -302,15 +303,15 @@ k_forward_residual(const __grid_constant__ CUtensorMap xmap, const float* __rest
 // blocking and the fill warps sleep on in hardware (no spin, no issue slots).  The fill of copy k+1 thus
 // overlaps the gather of copy k and the gather warps carry no bookkeeping at all.
 // Bounding boxes and the inverse transforms of a chunk of 128 copies are computed once into shared
-// memory (one thread per copy) before the roles split.
+// memory (one thread per copy, by the gather side); the roles part for good right after the CTA's set-up.
 constexpr int K2_T = 64;               // HR tile width; the tile height TY is 64 for batches that fill the GPU and 32 for one or two images
                                        // (one 512^2 image is only 64 tiles of 64x64: such a solve is latency-bound, 104 -> 79 us per iteration)
 #ifndef ASR_K2_GW
 #define ASR_K2_GW 8
 #endif
 constexpr int K2_GW = ASR_K2_GW;       // gather warps; thread owns pixels (lane + 32c, warp + 8r), c<2, r<TY/8
-// fill warps: 4 in the throughput variant (64-row tiles, two CTAs per SM); 8 in the latency variant (32-row tiles, one lone CTA per
-// SM, where the fill warps' serial latency per copy is what the gather warps wait for)
+// non-gather warps: 8 in both variants (7 fill + 1 producer): the throughput variant (64-row tiles, two CTAs per SM) and the
+// latency variant (32-row tiles, one lone CTA per SM, where the fill's serial latency per copy is what the gather warps wait for)
 #ifndef ASR_K2_FW64
 #define ASR_K2_FW64 8
 #endif
