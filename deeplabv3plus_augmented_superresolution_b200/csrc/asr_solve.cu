@@ -685,8 +685,18 @@ k_gradient_update(const __grid_constant__ CUtensorMap rmap, const float* __restr
     const bool need0 = !WRITE_GRAD && !(P.optimizer == ASR_OPT_SGD && P.momentum == 0.0f);
     const bool need1 = !WRITE_GRAD && (P.optimizer == ASR_OPT_ADAM || P.optimizer == ASR_OPT_ADADELTA || P.optimizer == ASR_OPT_ADAMAX);
     const bool need2 = !WRITE_GRAD && P.optimizer == ASR_OPT_ADAM && P.amsgrad;
-    constexpr int EB = 2;
+    // The accumulators go through shared memory (each thread reads back only what it wrote: no barrier) so that the batches can be a
+    // real loop: fully unrolled, the epilogue was ~2000 instructions per thread executed once per tile, an instruction-cache miss
+    // per line on top of its memory round trips.  The staging ring is free by now: the last fill finished before the last gather began.
+    float* gs = reinterpret_cast<float*>(stages);
+    static_assert(sizeof(K2Stage) * K2_STAGES >= sizeof(float) * TY * K2_T, "accumulator staging does not fit the stage ring");
 #pragma unroll
+    for (int r = 0; r < K2_ROWS; ++r) {
+        gs[(warp + K2_GW * r) * K2_T + lane] = pk_lo(accp[r]);
+        gs[(warp + K2_GW * r) * K2_T + lane + 32] = pk_hi(accp[r]);
+    }
+    constexpr int EB = 2;
+#pragma unroll 1
     for (int r0 = 0; r0 < K2_ROWS; r0 += EB) {
         float xi_[EB][2], nu_[EB][2], nl_[EB][2], nd_[EB][2], nr_[EB][2], v0_[EB][2], v1_[EB][2], v2_[EB][2];
 #pragma unroll
@@ -715,7 +725,7 @@ k_gradient_update(const __grid_constant__ CUtensorMap rmap, const float* __restr
                 if (X >= W || Y >= H) continue;
                 const size_t i = (size_t)Y * W + X;
                 const float xi = xi_[rr][c];
-                float g = c ? pk_hi(accp[r]) : pk_lo(accp[r]);
+                float g = gs[(warp + K2_GW * r) * K2_T + lane + 32 * c];
                 if (btv) {
                     // bilateral TV: 15 integer shifts (h in [-2,2], v in [0,2]) by nearest translate with zero fill;
                     // d/dx of w*|x - S(x)| is w*sign(d) here minus the same term pulled back by the inverse shift
