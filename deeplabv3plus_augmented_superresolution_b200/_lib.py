@@ -55,6 +55,9 @@ SIGNATURES = {
     "asr_solve_batched": (C.c_int, [C.POINTER(AsrSolveParams), C.c_int, C.c_void_p, _fp, _fp, _u8p,
                                     C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                     C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "asr_solve_batched_traced": (C.c_int, [C.POINTER(AsrSolveParams), C.c_int, C.c_void_p, _fp, _fp, _u8p,
+                                           C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                           C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p]),
     "asr_solve_sweep": (C.c_int, [C.POINTER(AsrSolveParams), C.c_int, C.c_void_p, _fp, _fp, C.POINTER(C.c_int32),
                                   C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                   C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
@@ -182,10 +185,11 @@ _aux_ws = Workspace()      # scratch of the warp / back-projection calls (kept a
 
 
 def solve_batched(copies, angles, shifts, params, keep=None, want_loss: bool = False, workspace: Optional[Workspace] = None,
-                  output_size=None):
+                  output_size=None, loss_every: int = 0):
     """asr_solve_batched.  copies: CUDA float32 tensor [B,N,h,w]; angles [B,N], shifts [B,N,2] host arrays;
     params: SolveParams or a list of B of them; output_size (H, W) defaults to (4h, 4w), the reference callers' shape (any even
-    integer ratio is accepted).  Returns x [B,H,W] (CUDA) and, if asked, loss [B] (CUDA)."""
+    integer ratio is accepted); loss_every > 0 also returns the verbose trace [B, ceil(max_iter/loss_every)] (asr_solve_batched_traced).
+    Returns x [B,H,W] (CUDA) and, if asked, loss [B] (CUDA), then the trace."""
     torch = _torch()
     L = lib()
     assert copies.is_cuda and copies.dtype == torch.float32 and copies.is_contiguous() and copies.dim() == 4
@@ -201,6 +205,15 @@ def solve_batched(copies, angles, shifts, params, keep=None, want_loss: bool = F
     ws = (workspace or _default_ws).get(need.value, copies.device)
     x = torch.empty((B, H, W), dtype=torch.float32, device=copies.device)
     loss = torch.empty((B,), dtype=torch.float32, device=copies.device) if want_loss else None
+    if loss_every > 0:
+        cols = -(-max_iter // int(loss_every))
+        trace = torch.full((B, max(cols, 1)), float("nan"), dtype=torch.float32, device=copies.device)
+        with torch.cuda.device(copies.device):
+            check(L.asr_solve_batched_traced(arr, n, copies.data_ptr(), ang.ctypes.data_as(_fp), shf.ctypes.data_as(_fp),
+                                             None if kp is None else kp.ctypes.data_as(_u8p), B, N, h, w, H, W,
+                                             x.data_ptr(), None if loss is None else loss.data_ptr(), int(loss_every),
+                                             trace.data_ptr(), trace.shape[1], ws.data_ptr(), ws.numel(), _stream_ptr(torch)))
+        return (x, loss, trace) if want_loss else (x, trace)
     with torch.cuda.device(copies.device):
         check(L.asr_solve_batched(arr, n, copies.data_ptr(), ang.ctypes.data_as(_fp), shf.ctypes.data_as(_fp),
                                   None if kp is None else kp.ctypes.data_as(_u8p), B, N, h, w, H, W,

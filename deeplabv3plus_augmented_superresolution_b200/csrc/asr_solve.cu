@@ -882,12 +882,16 @@ kg_gradient_update(const float* __restrict__ x_cur, float* __restrict__ x_next, 
 // ================================================================================================
 // loss of one evaluation (superresolution.py:71-98), double accumulators
 // ================================================================================================
+// at_iter < 0: the last evaluation of every image (x in buffer (num_iter-1)&1); at_iter >= 0: the evaluation of iteration at_iter
+// (the verbose trace of superresolution.py:129-130), images that have already finished are skipped.
 __global__ void k_loss_terms(const float* __restrict__ xa, const float* __restrict__ xb_, const float* __restrict__ resid,
-                             const ImgParams* __restrict__ ip, double* __restrict__ accum, int N, int h, int w, int wp, int H, int W) {
+                             const ImgParams* __restrict__ ip, double* __restrict__ accum, int N, int h, int w, int wp, int H, int W,
+                             int at_iter) {
     const int b = blockIdx.y;
     const ImgParams P = ip[b];
-    // x of the last evaluation lives in buffer (num_iter-1)&1
-    const float* x = (((P.num_iter - 1) & 1) ? xb_ : xa) + (size_t)b * H * W;
+    if (at_iter >= P.num_iter) return;
+    const int ev = at_iter >= 0 ? at_iter : P.num_iter - 1;
+    const float* x = ((ev & 1) ? xb_ : xa) + (size_t)b * H * W;
     const float* r = resid + (size_t)b * N * h * wp;
     const size_t nr = (size_t)P.n_kept * h * wp, nx = (size_t)H * W;
     double df = 0.0, tv = 0.0, l2 = 0.0, l1 = 0.0;
@@ -922,14 +926,15 @@ __global__ void k_loss_terms(const float* __restrict__ xa, const float* __restri
 }
 
 __global__ void k_loss_final(const double* __restrict__ accum, const AsrSolveParams* __restrict__ hp,
-                             float* __restrict__ loss, int B) {
+                             float* __restrict__ loss, int B, int stride, int at_iter) {
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= B) return;
     const AsrSolveParams p = hp[b];
+    if (at_iter >= p.num_iter) return;
     float l = fadd(fmul(p.lambda_df, (float)accum[4 * b]), fmul(p.lambda_tv, (float)accum[4 * b + 1]));
     l = fadd(l, fmul(p.lambda_l2, (float)accum[4 * b + 2]));
     if (p.lambda_l1 > 0.0f) l = fadd(l, fmul(p.lambda_l1, (float)accum[4 * b + 3]));
-    loss[b] = l;
+    loss[(size_t)b * stride] = l;
 }
 
 __global__ void k_select_output(const float* __restrict__ xa, const float* __restrict__ xb_, const ImgParams* __restrict__ ip,
@@ -1179,11 +1184,15 @@ static int configure_kernels() {
     return ASR_OK;
 }
 
-static int launch_loss(const Device& D, int n_params, float* d_loss, int B, int N, int h, int w, int H, int W, cudaStream_t st) {
-    ASR_CUDA_TRY(cudaMemsetAsync(D.accum, 0, sizeof(double) * 4 * B, st));
-    ASR_LAUNCH(k_loss_terms, dim3(64, B), 256, 0, st, D.xa, D.xb, D.resid, D.ip, D.accum, N, h, w, pitch4(w), H, W);
-    ASR_LAUNCH(k_loss_final, (B + 127) / 128, 128, 0, st, D.accum, D.hp, d_loss, B);   // D.hp is expanded to one entry per image
-    (void)n_params;
+// loss of images [b0, b0+nb): the last evaluation (at_iter < 0) into d_loss[b], or the evaluation of iteration at_iter into
+// d_loss[b * stride] (d_loss already points at the trace column)
+static int launch_loss(const Device& D, float* d_loss, int b0, int nb, int N, int h, int w, int H, int W, cudaStream_t st,
+                       int stride = 1, int at_iter = -1) {
+    const size_t plane = (size_t)H * W;
+    ASR_CUDA_TRY(cudaMemsetAsync(D.accum + 4 * (size_t)b0, 0, sizeof(double) * 4 * nb, st));
+    ASR_LAUNCH(k_loss_terms, dim3(64, nb), 256, 0, st, D.xa + b0 * plane, D.xb + b0 * plane, D.resid + (size_t)b0 * N * h * pitch4(w), D.ip + b0,
+               D.accum + 4 * (size_t)b0, N, h, w, pitch4(w), H, W, at_iter);
+    ASR_LAUNCH(k_loss_final, (nb + 127) / 128, 128, 0, st, D.accum + 4 * (size_t)b0, D.hp + b0, d_loss + (size_t)b0 * stride, nb, stride, at_iter);   // D.hp: one entry per image
     return ASR_OK;
 }
 
@@ -1239,11 +1248,13 @@ static int k2_tile_height(int n_images, int H, int W) {
 
 static int solve_impl(const AsrSolveParams* params, int n_params, const float* d_copies, const float* h_angles,
                       const float* h_shifts, const uint8_t* h_keep, const int32_t* h_stack_index, int B, int N, int h, int w,
-                      int H, int W, float* d_x_out, float* d_loss_out, void* d_workspace, size_t workspace_bytes, void* stream) {
+                      int H, int W, float* d_x_out, float* d_loss_out, void* d_workspace, size_t workspace_bytes, void* stream,
+                      int loss_every = 0, float* d_loss_trace = nullptr, int trace_cols = 0) {
     if (!params || !d_copies || !h_angles || !h_shifts || !d_x_out || !d_workspace) return fail(ASR_ENULL, "null argument");
     if (n_params != 1 && n_params != B) return fail(ASR_EINVAL, "n_params must be 1 or B");
     if (int e = check_shapes(B, N, h, w, H, W)) return e;
     if (int e = check_params(params, n_params)) return e;
+    if (loss_every < 0 || (loss_every > 0 && (!d_loss_trace || trace_cols <= 0))) return fail(ASR_EINVAL, "loss trace needs loss_every > 0, a buffer and trace_cols > 0");
     if (!aligned16(d_copies) || !aligned16(d_x_out) || (reinterpret_cast<uintptr_t>(d_workspace) & 255u))
         return fail(ASR_EINVAL, "d_copies / d_x_out must be 16-byte aligned and d_workspace 256-byte aligned");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -1264,6 +1275,11 @@ static int solve_impl(const AsrSolveParams* params, int n_params, const float* d
     ASR_LAUNCH(k_init_upsample, dim3((W + 31) / 32, (H + 7) / 8, B), dim3(32, 8), 0, st, d_copies, D.ip, D.xa, N, h, w, H, W);
 
     const int wp = pitch4(w);
+    // verbose trace (superresolution.py:129-130): the loss of iteration `it`, evaluated between the forward and the update kernel
+    auto trace_loss = [&](int b0, int nb, int it) -> int {
+        if (loss_every <= 0 || it % loss_every != 0 || it / loss_every >= trace_cols) return ASR_OK;
+        return launch_loss(D, d_loss_trace + it / loss_every, b0, nb, N, h, w, H, W, st, trace_cols, it);
+    };
     if (H != 4 * h) {
         // any other even ratio (x2, x6, x8 ...): the literal one-thread-per-output kernels
         const int S = H / h;
@@ -1272,12 +1288,13 @@ static int solve_impl(const AsrSolveParams* params, int n_params, const float* d
             float* xn = (it & 1) ? D.xa : D.xb;
             ASR_LAUNCH_TIMED(0, kg_forward_residual, dim3((h * w + 127) / 128, T.max_kept, B), 128, 0, st, xc, d_copies, D.resid, D.fwd, D.src,
                              D.ip, it, N, h, w, wp, H, W);
+            if (int e = trace_loss(0, B, it)) return e;
             ASR_LAUNCH_TIMED(1, kg_gradient_update<false>, dim3((H * W + 127) / 128, B), 128, 0, st, xc, xn, D.s0, D.s1, D.s2, D.resid, D.inv,
                              D.ip, D.sched, it, N, h, w, wp, H, W, B, S);
         }
         ASR_CUDA_TRY(cudaGetLastError());
         if (d_loss_out) {
-            if (int e = launch_loss(D, n_params, d_loss_out, B, N, h, w, H, W, st)) return e;
+            if (int e = launch_loss(D, d_loss_out, 0, B, N, h, w, H, W, st)) return e;
         }
         ASR_LAUNCH(k_select_output, dim3(32, B), 256, 0, st, D.xa, D.xb, D.ip, d_x_out, plane);
         ASR_CUDA_TRY(cudaGetLastError());
@@ -1329,12 +1346,13 @@ static int solve_impl(const AsrSolveParams* params, int n_params, const float* d
         const Group G = make_group(b0, nb);
         for (int it = 0; it < G.iters; ++it) {
             if (int e = launch_k1(G, it, st)) return e;
+            if (int e = trace_loss(b0, nb, it)) return e;
             if (int e = launch_k2(G, it, st)) return e;
         }
     }
     ASR_CUDA_TRY(cudaGetLastError());
     if (d_loss_out) {
-        if (int e = launch_loss(D, n_params, d_loss_out, B, N, h, w, H, W, st)) return e;
+        if (int e = launch_loss(D, d_loss_out, 0, B, N, h, w, H, W, st)) return e;
     }
     ASR_LAUNCH(k_select_output, dim3(32, B), 256, 0, st, D.xa, D.xb, D.ip, d_x_out, plane);
     ASR_CUDA_TRY(cudaGetLastError());
@@ -1347,6 +1365,14 @@ extern "C" int asr_solve_batched(const AsrSolveParams* params, int n_params, con
                                  size_t workspace_bytes, void* stream) {
     return solve_impl(params, n_params, d_copies, h_angles, h_shifts, h_keep, nullptr, B, N, h, w, H, W, d_x_out, d_loss_out,
                       d_workspace, workspace_bytes, stream);
+}
+
+extern "C" int asr_solve_batched_traced(const AsrSolveParams* params, int n_params, const float* d_copies, const float* h_angles,
+                                        const float* h_shifts, const uint8_t* h_keep, int B, int N, int h, int w, int H, int W,
+                                        float* d_x_out, float* d_loss_out, int loss_every, float* d_loss_trace, int trace_cols,
+                                        void* d_workspace, size_t workspace_bytes, void* stream) {
+    return solve_impl(params, n_params, d_copies, h_angles, h_shifts, h_keep, nullptr, B, N, h, w, H, W, d_x_out, d_loss_out,
+                      d_workspace, workspace_bytes, stream, loss_every, d_loss_trace, trace_cols);
 }
 
 extern "C" int asr_solve_sweep(const AsrSolveParams* params, int n_points, const float* d_copies, const float* h_angles,
@@ -1416,7 +1442,7 @@ extern "C" int asr_loss_grad_batched(const AsrSolveParams* params, int n_params,
                                                cudaMemcpyDeviceToDevice, st));
     }
     if (d_loss_out) {
-        if (int e = launch_loss(D, n_params, d_loss_out, B, N, h, w, H, W, st)) return e;
+        if (int e = launch_loss(D, d_loss_out, 0, B, N, h, w, H, W, st)) return e;
     }
     return ASR_OK;
 }

@@ -101,13 +101,19 @@ class Superresolution:
         self._check_sizes(h, w)
         keep = self._dropout_keep(n)
         params = self._solve_params(self.optimizer.iterations)
-        x, loss = _lib.solve_batched(stack[None], np.asarray(angles, np.float32)[None], np.asarray(shifts, np.float32)[None],
-                                     params, keep=None if keep is None else keep[None], want_loss=True, output_size=self.output_size)
+        res = _lib.solve_batched(stack[None], np.asarray(angles, np.float32)[None], np.asarray(shifts, np.float32)[None],
+                                 params, keep=None if keep is None else keep[None], want_loss=True, output_size=self.output_size,
+                                 loss_every=10 if self.verbose else 0)
+        x, loss = res[0], res[1]
         self.optimizer.iterations += int(self.num_iter)     # Keras' shared step counter keeps counting
         out = x[0].cpu().numpy()[..., None]
         loss = float(loss[0].item())
-        if self.verbose:
-            print(f"{self.num_iter}/{self.num_iter} -- loss = {loss}")
+        if self.verbose:   # reference :129-130: every tenth iteration and the last one (printed after the solve here, not during it)
+            trace = res[2][0].cpu().numpy()
+            for i in range(int(self.num_iter)):
+                if i % 10 == 0 or i == self.num_iter - 1:
+                    v = loss if i == self.num_iter - 1 else float(trace[i // 10])
+                    print(f"{i + 1}/{self.num_iter} -- loss = {v}")
         return out, loss
 
     def max_superresolution(self, augmented_copies, angles, shifts):

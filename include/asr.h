@@ -105,6 +105,16 @@ int asr_solve_batched(const AsrSolveParams* params, int n_params,
                       float* d_x_out, float* d_loss_out,
                       void* d_workspace, size_t workspace_bytes, void* stream);
 
+/* The same solve with the reference's verbose trace (superresolution.py:129-130 prints the loss every 10 iterations):
+ * d_loss_trace [B, trace_cols] receives, in column j, the loss of iteration j*loss_every evaluated on the iterate BEFORE that
+ * iteration's update (the value the reference prints as "{j*loss_every+1}/{num_iter}"); columns past an image's num_iter are
+ * left untouched.  Each traced iteration costs one extra reduction over the residuals and x.                              */
+int asr_solve_batched_traced(const AsrSolveParams* params, int n_params,
+                             const float* d_copies, const float* h_angles, const float* h_shifts,
+                             const uint8_t* h_keep, int B, int N, int h, int w, int H, int W,
+                             float* d_x_out, float* d_loss_out, int loss_every, float* d_loss_trace, int trace_cols,
+                             void* d_workspace, size_t workspace_bytes, void* stream);
+
 /* Hyper-parameter sweeps (sweep_script.py:88-130, check_robustness-style grids): n_points independent
  * solves, point i using LR stack h_stack_index[i] of d_copies [n_stacks,N,h,w] (angles [n_stacks,N],
  * shifts [n_stacks,N,2]) with its own params[i]; many points may share one stack without copying it.

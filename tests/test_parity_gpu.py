@@ -600,3 +600,38 @@ def test_reference_class_default_feature_size_is_x8():
     np.testing.assert_array_equal(x, xo)
     with pytest.raises(NotImplementedError):
         Superresolution(1.0, 0.3, 0.7, 0.0, optimizer=Optimizer(), output_size=(96, 96))._check_sizes(32, 32)       # x3: odd ratio
+
+
+# --------------------------------------------------------------------------------------------------
+# verbose trace: the loss the reference prints every tenth iteration (superresolution.py:129-130)
+# --------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("S", [4, 8])
+def test_loss_trace_matches_oracle(S, capsys):
+    from deeplabv3plus_augmented_superresolution_b200.synthetic import make_augmented_copies
+    from deeplabv3plus_augmented_superresolution_b200.superresolution_scripts.optimizer import Optimizer
+    from deeplabv3plus_augmented_superresolution_b200.superresolution_scripts.superresolution import Superresolution
+    h = w = 16
+    copies, ang, sh = make_augmented_copies(2, 5, (h, w), (S * h, S * w), 0.2, 10, seed=71, device="cuda")
+    plist = [A.SolveParams(num_iter=25), A.SolveParams(num_iter=12, lambda_tv=0.1)]           # per-image iteration counts
+    x, loss, trace = A.solve_batched(copies, ang, sh, plist, want_loss=True, output_size=(S * h, S * w), loss_every=10)
+    assert trace.shape == (2, 3)
+    tr = trace.cpu().numpy()
+    cp = copies.cpu().numpy()
+    for b, kw in enumerate([dict(), dict(lambda_tv=0.1)]):
+        n_it = plist[b].num_iter
+        for j in range(3):
+            if 10 * j >= n_it:
+                assert np.isnan(tr[b, j])                                                   # untouched: the image had finished
+                continue
+            _, lo = O.augmented_superresolution(cp[b], ang[b], sh[b], O.SolveParams(num_iter=10 * j + 1, **kw), output_size=(S * h, S * w))
+            assert_loss_close(float(tr[b, j]), lo)
+        xo, lo = O.augmented_superresolution(cp[b], ang[b], sh[b], O.SolveParams(num_iter=n_it, **kw), output_size=(S * h, S * w))
+        assert np.array_equal(x[b].cpu().numpy(), xo[..., 0])                               # tracing does not disturb the solve
+        assert_loss_close(float(loss[b]), lo)
+    # the reference-named call prints every tenth iteration and the last one
+    sr = Superresolution(1.0, 0.3, 0.7, 0.0, num_iter=25, num_aug=5, optimizer=Optimizer(amsgrad=True, lr_scheduler=True, decay_steps=60, decay_rate=0.3),
+                         feature_size=(h, w), output_size=(S * h, S * w), verbose=True)
+    sr.augmented_superresolution(cp[0][..., None], ang[0], sh[0])
+    lines = [l for l in capsys.readouterr().out.splitlines() if " -- loss = " in l]
+    assert [l.split(" -- ")[0] for l in lines] == ["1/25", "11/25", "21/25", "25/25"]
+    assert abs(float(lines[1].split("= ")[1]) - float(tr[0, 1])) <= 1e-5 * abs(float(tr[0, 1]))
