@@ -62,6 +62,18 @@ def test_workspace_query_and_error_codes(L):
     assert L.asr_solve_batched(*args(pb, 1)) == -1 and b"optimizer" in L.asr_last_error()
     assert L.asr_solve_batched(None, 1, fake, ang.ctypes.data_as(_lib._fp), shf.ctypes.data_as(_lib._fp), None,
                                1, 4, 16, 16, 64, 64, fake, None, fake, 1 << 30, None) == -2
+    # the traced form validates its extra arguments before anything else touches the device
+    tr = lambda every, buf, cols: L.asr_solve_batched_traced(C.byref(p), 1, fake, ang.ctypes.data_as(_lib._fp), shf.ctypes.data_as(_lib._fp), None,
+                                                             1, 4, 16, 16, 64, 64, fake, None, every, buf, cols, fake, 1 << 30, None)
+    assert tr(10, None, 3) == -1 and b"loss trace" in L.asr_last_error()
+    assert tr(-1, fake, 3) == -1 and tr(10, fake, 0) == -1
+    # workspace queries of the aux calls
+    need2 = C.c_size_t()
+    assert L.asr_warp_affine_workspace_bytes(100, 512, 512, 3, C.byref(need2)) == 0 and need2.value >= 512 * 512 * 16 + 100 * 32
+    assert L.asr_warp_affine_workspace_bytes(100, 512, 512, 5, C.byref(need2)) == -1
+    assert L.asr_backproject_workspace_bytes(8, 100, C.byref(need2)) == 0 and need2.value >= 8 * 100 * 32
+    assert L.asr_backproject_workspace_bytes(0, 100, C.byref(need2)) == -1 and L.asr_backproject_workspace_bytes(8, 100, None) == -2
+    assert L.asr_l2_read_probe(None, 1 << 20, 2, fake, None) == -2 and L.asr_l2_read_probe(fake, 8, 2, fake, None) == -1
     with pytest.raises(NotImplementedError):
         _lib.check(-3)
     with pytest.raises(_lib.AsrError):
