@@ -318,6 +318,9 @@ constexpr int K2_GW = ASR_K2_GW;       // gather warps; thread owns pixels (lane
 #ifndef ASR_K2_AHEAD
 #define ASR_K2_AHEAD 3
 #endif
+#ifndef ASR_K2_FILLERS      // fill warps of the throughput variant; measured (us per image-iteration): 4: 30.0, 5: 30.5, 6: 30.4, 7: 28.1
+#define ASR_K2_FILLERS 7
+#endif
 #ifndef ASR_K2_PRODUCER
 #define ASR_K2_PRODUCER 1
 #endif
@@ -327,7 +330,8 @@ constexpr int K2_GW = ASR_K2_GW;       // gather warps; thread owns pixels (lane
 template <int TY> struct K2Fill {
     static constexpr int warps = TY == 64 ? ASR_K2_FW64 : 8, threads = 32 * (K2_GW + warps), ctas = TY == 64 ? 2 : 1;
     static constexpr bool producer = ASR_K2_PRODUCER && warps == 8;
-    static constexpr int fillers = producer ? warps - 1 : warps;
+    static constexpr int fillers = producer ? (TY == 64 ? ASR_K2_FILLERS : warps - 1) : warps;   // warps beyond fillers + producer leave at once
+    static constexpr int part = 32 * (K2_GW + fillers + (producer ? 1 : 0));                   // threads that take part in the barriers
 };
 // The throughput variant (64-row tiles, two CTAs per SM) runs 8 gather warps + 7 fill warps + 1 producer warp with a register split
 // between the roles (setmaxnreg, per warpgroup of 4 warps): with 16 warps and two CTAs per SM the launch gives every thread 64
@@ -468,7 +472,8 @@ k_gradient_update(const __grid_constant__ CUtensorMap rmap, const float* __restr
     const int b = blockIdx.y;
     const ImgParams P = ip[b];
     if (it >= P.num_iter) return;
-    constexpr int K2_UR = K2Rows<TY>::value, K2_ROWS = TY / K2_GW, K2_FW = K2Fill<TY>::warps, K2_THREADS = K2Fill<TY>::threads;
+    constexpr int K2_UR = K2Rows<TY>::value, K2_ROWS = TY / K2_GW;
+    constexpr int K2_PART = K2Fill<TY>::part;   // threads that take part in the chunk barriers and the "empty" hand-off
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float* ut = reinterpret_cast<float*>(smem_raw);                       // [2][K2_UR][K2_US]
     K2Stage* stages = reinterpret_cast<K2Stage*>(ut + 2 * K2_US * K2_UR);  // [K2_STAGES]
@@ -503,7 +508,7 @@ k_gradient_update(const __grid_constant__ CUtensorMap rmap, const float* __restr
     const bool gather_role = warp < K2_GW;
 
     // tile rows 3 (mod 4) hold phase 3 of every cell: zero for every copy
-    for (int i = tid; i < 2 * (K2_UR / 4) * (K2_US / 4); i += K2_THREADS) {
+    for (int i = tid; i < 2 * (K2_UR / 4) * (K2_US / 4) && tid < K2_PART; i += K2_PART) {
         const int row = i / (K2_US / 4), c4 = i - row * (K2_US / 4);
         reinterpret_cast<float4*>(ut + (4 * row + 3) * K2_US)[c4] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);   // rows of buffer 1 follow buffer 0
     }
@@ -511,11 +516,12 @@ k_gradient_update(const __grid_constant__ CUtensorMap rmap, const float* __restr
     // The roles part here and never meet again except at the chunk barriers (bar 0, every thread, twice per chunk), so that each
     // side can be compiled and run with its own register budget.
     if (!gather_role) {
-        if (TY == 64 && K2_REG_SPLIT) asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+        if (TY == 64 && K2_REG_SPLIT) asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");   // every warp of both warpgroups, same instruction
+        if (tid >= K2_PART) return;   // warps beyond the fill warps and the producer only exist to make whole warpgroups
         for (int k0 = 0; k0 < nk; k0 += K2_CHUNK) {
             const int nc = min(K2_CHUNK, nk - k0);
-            __syncthreads();   // the previous chunk's boxes are no longer read
-            __syncthreads();   // this chunk's boxes and transforms are in place (written by the gather warps)
+            bar_sync(0, K2_PART);   // the previous chunk's boxes are no longer read
+            bar_sync(0, K2_PART);   // this chunk's boxes and transforms are in place (written by the gather warps)
             // =================== fill warps ===================
             // Warp fw owns the cell rows fw, fw+4, ... of the box and lane l the cell column l (boxes are at most 24
             // cells wide).  Everything the fill reads was staged by async copies issued two copies earlier by one
@@ -523,7 +529,7 @@ k_gradient_update(const __grid_constant__ CUtensorMap rmap, const float* __restr
             const int fw = warp - K2_GW;
             constexpr int K2_FILLERS = K2Fill<TY>::fillers;
             constexpr int ROWS = (K2_UR / 4 + K2_FILLERS - 1) / K2_FILLERS;   // cell rows per fill warp
-            const bool is_producer = K2Fill<TY>::producer && fw == K2_FW - 1;
+            const bool is_producer = K2Fill<TY>::producer && fw == K2_FILLERS;   // the warp right after the fill warps
             const size_t slot0 = (size_t)(b_base + b) * N + k0;
             const int ncw = w + 2 * K2_TPAD, nrw = h + 2 * K2_TPAD;
             auto stage_copy = [&](int kq) {   // one thread: residual box + tap rows of copy kq -> stage (k0+kq) % 4
@@ -543,7 +549,7 @@ k_gradient_update(const __grid_constant__ CUtensorMap rmap, const float* __restr
                 const bool live = !(bc.ncxy >> 16);
                 const int ncx = bc.ncxy & 0xff, ncy = (bc.ncxy >> 8) & 0xff;
                 K2_TR(0);
-                if (kc >= 2) { if (ub) bar_sync(BAR_EMPTY + 1, K2_THREADS); else bar_sync(BAR_EMPTY, K2_THREADS); }   // the gather of copy kc-2 has left this buffer
+                if (kc >= 2) { if (ub) bar_sync(BAR_EMPTY + 1, K2_PART); else bar_sync(BAR_EMPTY, K2_PART); }   // the gather of copy kc-2 has left this buffer
                 // Keep the staging K2_AHEAD copies ahead.  Copy q reuses the stage of copy q-4, which is free once every fill warp
                 // has finished q-4: true when q-4 < 0 (the chunk's first use; the previous chunk ended with __syncthreads) or
                 // when the barrier above was passed (kc >= 2: every fill warp arrived for kc, i.e. is done with kc-1 >= q-4).
@@ -598,7 +604,7 @@ k_gradient_update(const __grid_constant__ CUtensorMap rmap, const float* __restr
 
     for (int k0 = 0; k0 < nk; k0 += K2_CHUNK) {
         const int nc = min(K2_CHUNK, nk - k0);
-        __syncthreads();   // the previous chunk's boxes are no longer read
+        bar_sync(0, K2_PART);   // the previous chunk's boxes are no longer read
         // ---- chunk prologue: bounding box of Rinv(tile) for each copy (one thread per copy).  Each
         //      rounded op of the coordinate is monotone in X and Y: the four corners bound every tap.
         if (tid < nc) {
@@ -630,7 +636,7 @@ k_gradient_update(const __grid_constant__ CUtensorMap rmap, const float* __restr
             boxes[tid] = bx;
             xfs[tid] = T;
         }
-        __syncthreads();
+        bar_sync(0, K2_PART);
 
         // =================== gather warps ===================
         K2_TM(1);
@@ -670,7 +676,7 @@ k_gradient_update(const __grid_constant__ CUtensorMap rmap, const float* __restr
             }
             K2_TR(2);
             // hand the buffer back; the last two hand-backs of a chunk have no taker
-            if (kc + 2 < nc) { if (kc & 1) bar_arrive(BAR_EMPTY + 1, K2_THREADS); else bar_arrive(BAR_EMPTY, K2_THREADS); }
+            if (kc + 2 < nc) { if (kc & 1) bar_arrive(BAR_EMPTY + 1, K2_PART); else bar_arrive(BAR_EMPTY, K2_PART); }
         }
     }
     K2_TM(2);
