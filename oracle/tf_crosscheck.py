@@ -10,6 +10,13 @@ inputs the goldens use, and reports oracle-vs-TensorFlow max-abs per stage:
 
 Usage:
     python oracle/tf_crosscheck.py --reference /path/to/DeepLabV3Plus-Augmented-SuperResolution [--device cpu]
+                                   [--write-golden tests/golden/tf_crosscheck.npz] [--write-hdf5 tests/golden/h5py_fixture.hdf5]
+
+--write-golden stores the TensorFlow-produced vectors (inputs, transform matrices and inverses from tfa's helpers, loss, gradient,
+x after 1 / 10 / num_iter steps); tests/test_oracle.py::test_tf_generated_goldens then pins the oracle to them on every run.
+--write-hdf5 writes one augmented-copies file with real h5py exactly as augmentation_utils.py:123-136 does;
+tests/test_host.py::test_hdf5_reader_on_h5py_fixture then pins hdf5_lite's reader to it.  Neither file exists in this repo yet:
+the attempt to install TensorFlow / h5py on the build and GPU images is logged in profiles/r02_tf_install_attempt.log.
 
 Expected outcome if the operator semantics of SURVEY.md Appendix A are right: residual and gradient agree to
 fp32 rounding (<= ~1e-5 relative); x after many steps agrees to the fp32 "chaos floor" measured in
@@ -33,6 +40,8 @@ def main():
     ap.add_argument("--num-aug", type=int, default=20)
     ap.add_argument("--lr-size", type=int, default=64)
     ap.add_argument("--iters", type=int, default=60)
+    ap.add_argument("--write-golden", default=None)
+    ap.add_argument("--write-hdf5", default=None)
     args = ap.parse_args()
     if args.device == "cpu":
         os.environ["CUDA_VISIBLE_DEVICES"] = ""
@@ -67,6 +76,20 @@ def main():
     print(f"loss        tf {float(loss):.6f}  oracle {lo:.6f}")
     print(f"gradient    max-abs {np.abs(g_tf - g_o).max():.3e}  rel-L2 {np.linalg.norm(g_tf - g_o) / np.linalg.norm(g_tf):.3e}")
 
+    gold = {"copies": c, "angles": a, "shifts": s, "H": H, "loss_tf": np.float32(loss), "grad_tf": g_tf, "iters": np.int32(args.iters)}
+    try:   # the transform helpers the reference reaches through tfa.image.rotate / translate, and tf.linalg.inv of the 3x3
+        import tensorflow_addons as tfa
+        rot = tfa.image.angles_to_projective_transforms(tf.constant(a), float(H), float(H)).numpy()
+        tr = tfa.image.translations_to_projective_transforms(tf.constant(s)).numpy()
+        def inv8(t):
+            m = tf.reshape(tf.concat([t, tf.ones((t.shape[0], 1), tf.float32)], 1), (-1, 3, 3))
+            mi = tf.linalg.inv(m)
+            return (tf.reshape(mi, (-1, 9)) / mi[:, 2, 2, None])[:, :8].numpy()
+        gold.update(rot_tf=rot, tr_tf=tr, rot_inv_tf=inv8(tf.constant(rot)), tr_inv_tf=inv8(tf.constant(tr)))
+        print(f"rotate matrices  max-abs vs oracle {max(np.abs(rot[k] - O.rotate_matrix(a[k], H, H)).max() for k in range(len(a))):.3e}")
+    except Exception as e:   # tfa may be missing where core TF exists
+        print("tensorflow_addons helpers unavailable:", e)
+
     # stage 2: iterates
     for n in (1, 10, args.iters):
         x_tf, _ = ref_solver(n).augmented_superresolution(tf.constant(c[..., None]), a, s)
@@ -76,6 +99,23 @@ def main():
         m_o = O.threshold_image(x_o, 8, th_factor=0.65)
         print(f"x after {n:4d}  max-abs {d.max():.3e}  mean-abs {d.mean():.3e}  pixels>1e-4 {(d > 1e-4).sum()}  "
               f"mask agreement {(m_tf == m_o).mean():.6f}")
+        gold[f"x_tf_{n}"] = np.asarray(x_tf, np.float32)
+    if args.write_golden:
+        np.savez_compressed(args.write_golden, **gold)
+        print("wrote", args.write_golden)
+    if args.write_hdf5:
+        import h5py
+        f = h5py.File(args.write_hdf5, "w")                      # augmentation_utils.py:123-136, verbatim calls
+        f.create_dataset("class_masks", data=[m[..., None] for m in c])
+        f.create_dataset("angles", data=a)
+        f.create_dataset("shifts", data=s)
+        f.attrs["filename"] = "2007_000032"
+        f.attrs["mode"] = "argmax"
+        f.attrs["angle_max"] = 0.15
+        f.attrs["shift_max"] = 80
+        f.close()
+        np.save(args.write_hdf5 + ".class_masks.npy", np.stack([m[..., None] for m in c]))
+        print("wrote", args.write_hdf5)
 
 
 if __name__ == "__main__":

@@ -275,3 +275,17 @@ def test_hdf5_reader_on_a_spec_level_file_it_did_not_write(tmp_path):
     assert f.attrs["angle_max"] == 0.15 and f.attrs["shift_max"] == 80
     assert SU.check_hdf5_validity(f, num_aug=5) and not SU.check_hdf5_validity(f, num_aug=6)
     f.close()
+
+
+_H5PY_FIXTURE = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "h5py_fixture.hdf5")
+
+
+@pytest.mark.skipif(not os.path.exists(_H5PY_FIXTURE), reason="no h5py-written fixture in this repo yet (oracle/tf_crosscheck.py --write-hdf5; "
+                    "h5py cannot be installed here: profiles/r02_tf_install_attempt.log)")
+def test_hdf5_reader_on_h5py_fixture():
+    """A file written by real h5py with the reference's own calls (augmentation_utils.py:123-136), when one is committed."""
+    f = hdf5_lite.File(_H5PY_FIXTURE, "r")
+    want = np.load(_H5PY_FIXTURE + ".class_masks.npy")
+    np.testing.assert_array_equal(f["class_masks"][:len(want)], want)
+    assert f.attrs["filename"] == "2007_000032" and f.attrs["mode"] == "argmax" and f.attrs["angle_max"] == 0.15 and f.attrs["shift_max"] == 80
+    f.close()

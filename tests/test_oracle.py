@@ -196,3 +196,30 @@ def test_chaos_floor_is_documented(oracle):
     d = np.abs(a - b)
     assert d.max() > 1e-5           # not bit-identical, and amplified far beyond 1 ulp
     assert np.mean(d) < 1e-4        # but statistically the same solution
+
+
+_TF_GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "tf_crosscheck.npz")
+
+
+@pytest.mark.skipif(not os.path.exists(_TF_GOLDEN), reason="no TensorFlow-generated golden in this repo yet (oracle/tf_crosscheck.py --write-golden; "
+                    "TensorFlow cannot be installed here: profiles/r02_tf_install_attempt.log)")
+def test_tf_generated_goldens(oracle):
+    """The day a maintainer with tensorflow 2.7 + tfa 0.15 runs oracle/tf_crosscheck.py --write-golden, this pins the oracle to it."""
+    z = np.load(_TF_GOLDEN)
+    c, a, s, H = z["copies"], z["angles"], z["shifts"], int(z["H"])
+    if "rot_tf" in z.files:
+        for k in range(len(a)):
+            np.testing.assert_allclose(oracle.rotate_matrix(a[k], H, H), z["rot_tf"][k], atol=2e-5, rtol=1e-6)
+            np.testing.assert_allclose(oracle.invert_transform(z["rot_tf"][k]), z["rot_inv_tf"][k], atol=3e-4, rtol=1e-5)
+            np.testing.assert_array_equal(oracle.invert_transform(z["tr_tf"][k]), z["tr_inv_tf"][k])
+    x0 = oracle.resize_bilinear(c[:1, :, :, None], (H, H))[0, :, :, 0]
+    lo, g = oracle.loss_and_grad(x0, c, a, s, oracle.SolveParams())
+    assert abs(lo - float(z["loss_tf"])) <= 1e-5 * abs(lo)
+    assert np.linalg.norm(g - z["grad_tf"]) <= 1e-5 * np.linalg.norm(g)
+    for n in (1, 10, int(z["iters"])):
+        xo, _ = oracle.augmented_superresolution(c, a, s, oracle.SolveParams(num_iter=n), output_size=(H, H))
+        xt = z[f"x_tf_{n}"]
+        # x itself can only agree to the fp32 chaos floor (profiles/r01_chaos_floor.txt); the north-star gates that survive it:
+        assert np.mean(np.abs(xo - xt)) < 1e-4
+        m_o, m_t = oracle.threshold_image(xo, 8, th_factor=0.65), oracle.threshold_image(xt, 8, th_factor=0.65)
+        assert (m_o == m_t).mean() >= 0.999
