@@ -66,6 +66,8 @@ CASES = [
     dict(N=5, hw=(18, 22), iters=7, angle_max=0.4, shift_max=15, seed=14),                      # LR width not a multiple of 4: padded residual pitch
     dict(N=4, hw=(15, 17), iters=6, angle_max=1.2, shift_max=10, seed=15, value=8.0),           # odd sizes
     dict(N=131, hw=(16, 16), iters=3, angle_max=0.8, shift_max=30, seed=16),                    # odd copy count over two K2 chunks
+    dict(N=5, hw=(256, 256), iters=3, angle_max=0.15, shift_max=160, seed=17),                  # 1024^2 canvas: 256 forward tiles, 256 gradient tiles
+    dict(N=4, hw=(200, 72), iters=3, angle_max=1.0, shift_max=40, seed=18),                     # tall ragged canvas, big-box variant
 ]
 
 
