@@ -55,6 +55,21 @@ def _threshold_batched(x, class_id, th_factor, th_mask=None):
     return out
 
 
+def solve_class_and_max(sr: Superresolution, class_masks, max_masks, angles, shifts):
+    """compute_SR's slice_max branch (superres_utils.py:250-254: the class solve, then the max solve, on one shared optimizer)
+    as ONE two-image call: same step offsets, same results, both solves in flight together.  Returns two [H,W,1] float32 arrays."""
+    from .superresolution_scripts.superresolution import _as_device_stack
+    torch = _lib._torch()
+    cls, mx = _as_device_stack(class_masks), _as_device_stack(max_masks)
+    ang = np.asarray(angles, np.float32).reshape(1, -1)
+    shf = np.asarray(shifts, np.float32).reshape(1, -1, 2)
+    keep = sr._dropout_keep(cls.shape[0])
+    x = sr.augmented_superresolution_batched(torch.stack([cls, mx]).contiguous(), np.repeat(ang, 2, axis=0), np.repeat(shf, 2, axis=0),
+                                             keep=None if keep is None else np.stack([keep, keep]))
+    x = x.cpu().numpy()
+    return x[0][..., None], x[1][..., None]
+
+
 def solve_stacks(sr: Superresolution, class_stacks, max_stacks, angles, shifts, class_id, th_factor,
                  sr_types: Sequence[str] = ("aug", "max", "mean")) -> dict:
     """compute_SR for B images at once.  class_stacks: CUDA [B,N,h,w]; max_stacks: same shape or None;

@@ -194,15 +194,20 @@ def compute_SR(superresolution_obj: Superresolution, class_masks, angles, shifts
     elif SR_type == "max":
         SR_function = superresolution_obj.max_superresolution
 
-    target_image_class, _ = SR_function(class_masks, angles, shifts)
-
     n_max = 0 if max_masks is None else len(max_masks)       # reference :253 crashes on None (Appendix B-2)
     target_image_max = None
     if n_max == len(class_masks):
-        target_image_max, _ = SR_function(max_masks, angles, shifts)
+        if SR_type == "aug" and not superresolution_obj.verbose:
+            # the class solve and the max solve of this image as one two-image call (same step offsets, same results)
+            from ..batch_runner import solve_class_and_max
+            target_image_class, target_image_max = solve_class_and_max(superresolution_obj, class_masks, max_masks, angles, shifts)
+        else:
+            target_image_class, _ = SR_function(class_masks, angles, shifts)
+            target_image_max, _ = SR_function(max_masks, angles, shifts)
         th_mask = threshold_image(
             target_image_class, class_id, th_mask=target_image_max)
     else:
+        target_image_class, _ = SR_function(class_masks, angles, shifts)
         th_mask = threshold_image(
             target_image_class, class_id, th_factor=th_factor)
 
