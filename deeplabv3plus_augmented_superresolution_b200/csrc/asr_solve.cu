@@ -327,11 +327,8 @@ constexpr int K2_GW = ASR_K2_GW;       // gather warps; thread owns pixels (lane
 // non-gather warps of a CTA.  With 8 of them the last one is a PRODUCER: it only issues the async staging copies (the clock64
 // trace showed the issuing thread's ~800 clk per copy sitting on the fill's critical path when a fill warp did it), the other
 // seven fill.
-// TWO: two CTAs per SM (the 64-row throughput variant always; the 32-row tile also has a two-per-SM form for calls of two images,
-// e.g. compute_SR's class + max solves, whose 256 CTAs then all fit the GPU at once).
-template <int TY, bool TWO> struct K2Fill {
-    static constexpr int warps = TY == 64 ? ASR_K2_FW64 : 8, threads = 32 * (K2_GW + warps), ctas = TWO ? 2 : 1;
-    static constexpr bool reg_split = TWO && warps == 8 && K2_GW == 8;   // setmaxnreg: gather warpgroups 88, fill/producer warpgroups 40
+template <int TY> struct K2Fill {
+    static constexpr int warps = TY == 64 ? ASR_K2_FW64 : 8, threads = 32 * (K2_GW + warps), ctas = TY == 64 ? 2 : 1;
     static constexpr bool producer = ASR_K2_PRODUCER && warps == 8;
     static constexpr int fillers = producer ? (TY == 64 ? ASR_K2_FILLERS : warps - 1) : warps;   // warps beyond fillers + producer leave at once
     static constexpr int part = 32 * (K2_GW + fillers + (producer ? 1 : 0));                   // threads that take part in the barriers
@@ -342,6 +339,7 @@ template <int TY, bool TWO> struct K2Fill {
 // accumulators + 8-deep unrolled gather needs (8*88 + 8*40 = 16*64).  Measured (r02, us per image-iteration at 250 images):
 // 4 fill warps, staging 2 ahead 29.2; 8 fill warps 30.2 (no gain by itself: the loop is issue-bound); 7 fill + producer,
 // staging 3 ahead 28.4.  -DASR_K2_FW64=4 -DASR_K2_AHEAD=2 rebuilds the 12-warp variant.
+constexpr bool K2_REG_SPLIT = (ASR_K2_FW64 == 8) && (K2_GW == 8);
 constexpr int K2_AHEAD = ASR_K2_AHEAD;   // copies the async staging (residual box + tap rows) runs ahead of the fill (at most K2_STAGES - 1)
 constexpr int K2_NG = 32 * K2_GW;
 constexpr int K2_US = 96;              // u tile stride: 64*sqrt(2)+2+3 < 96, multiple of 32
@@ -465,8 +463,8 @@ __device__ long long g_k2_misc[16][4];
 #define K2_TM(slot) do {} while (0)
 #endif
 
-template <bool WRITE_GRAD, bool BTV, int TY, bool TWO>
-__global__ void __launch_bounds__((K2Fill<TY, TWO>::threads), (K2Fill<TY, TWO>::ctas))
+template <bool WRITE_GRAD, bool BTV, int TY>
+__global__ void __launch_bounds__(K2Fill<TY>::threads, K2Fill<TY>::ctas)
 k_gradient_update(const __grid_constant__ CUtensorMap rmap, const float* __restrict__ x_cur, float* __restrict__ x_next,
                   float* __restrict__ s0, float* __restrict__ s1, float* __restrict__ s2, const float2* __restrict__ tapc,
                   const float2* __restrict__ tapr, const InvXf* __restrict__ inv, const ImgParams* __restrict__ ip,
@@ -475,7 +473,7 @@ k_gradient_update(const __grid_constant__ CUtensorMap rmap, const float* __restr
     const ImgParams P = ip[b];
     if (it >= P.num_iter) return;
     constexpr int K2_UR = K2Rows<TY>::value, K2_ROWS = TY / K2_GW;
-    constexpr int K2_PART = K2Fill<TY, TWO>::part;   // threads that take part in the chunk barriers and the "empty" hand-off
+    constexpr int K2_PART = K2Fill<TY>::part;   // threads that take part in the chunk barriers and the "empty" hand-off
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float* ut = reinterpret_cast<float*>(smem_raw);                       // [2][K2_UR][K2_US]
     K2Stage* stages = reinterpret_cast<K2Stage*>(ut + 2 * K2_US * K2_UR);  // [K2_STAGES]
@@ -492,7 +490,7 @@ k_gradient_update(const __grid_constant__ CUtensorMap rmap, const float* __restr
     if (!WRITE_GRAD) {
         // the epilogue's operands (x, optimizer slots) are asked into the L2 now, a whole copy loop before they are needed
         constexpr int LINES = TY * (K2_T * 4 / 128);   // 128-byte lines per array per tile
-        for (int i = tid; i < 4 * LINES; i += K2Fill<TY, TWO>::threads) {
+        for (int i = tid; i < 4 * LINES; i += K2Fill<TY>::threads) {
             const int arr = i / LINES, l = i - arr * LINES, row = l / (K2_T * 4 / 128), seg = l - row * (K2_T * 4 / 128);
             const int X = tx0 + 32 * seg, Y = ty0 + row;
             if (X < W && Y < H) {
@@ -505,7 +503,7 @@ k_gradient_update(const __grid_constant__ CUtensorMap rmap, const float* __restr
     if (tid == 0) {
 #pragma unroll
         for (int i = 0; i < K2_STAGES; ++i) mbar_init(&stage_bar[i], 3);   // three async copies per stage
-        mbar_init(&full_bar[0], K2Fill<TY, TWO>::fillers); mbar_init(&full_bar[1], K2Fill<TY, TWO>::fillers);   // one arrival per fill warp
+        mbar_init(&full_bar[0], K2Fill<TY>::fillers); mbar_init(&full_bar[1], K2Fill<TY>::fillers);   // one arrival per fill warp
     }
     const bool gather_role = warp < K2_GW;
 
@@ -518,7 +516,7 @@ k_gradient_update(const __grid_constant__ CUtensorMap rmap, const float* __restr
     // The roles part here and never meet again except at the chunk barriers (bar 0, every thread, twice per chunk), so that each
     // side can be compiled and run with its own register budget.
     if (!gather_role) {
-        if (K2Fill<TY, TWO>::reg_split) asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");   // every warp of both warpgroups, same instruction
+        if (TY == 64 && K2_REG_SPLIT) asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");   // every warp of both warpgroups, same instruction
         if (tid >= K2_PART) return;   // warps beyond the fill warps and the producer only exist to make whole warpgroups
         for (int k0 = 0; k0 < nk; k0 += K2_CHUNK) {
             const int nc = min(K2_CHUNK, nk - k0);
@@ -529,9 +527,9 @@ k_gradient_update(const __grid_constant__ CUtensorMap rmap, const float* __restr
             // cells wide).  Everything the fill reads was staged by async copies issued two copies earlier by one
             // thread: no address arithmetic, bounds tests or table building is left in these warps.
             const int fw = warp - K2_GW;
-            constexpr int K2_FILLERS = K2Fill<TY, TWO>::fillers;
+            constexpr int K2_FILLERS = K2Fill<TY>::fillers;
             constexpr int ROWS = (K2_UR / 4 + K2_FILLERS - 1) / K2_FILLERS;   // cell rows per fill warp
-            const bool is_producer = K2Fill<TY, TWO>::producer && fw == K2_FILLERS;   // the warp right after the fill warps
+            const bool is_producer = K2Fill<TY>::producer && fw == K2_FILLERS;   // the warp right after the fill warps
             const size_t slot0 = (size_t)(b_base + b) * N + k0;
             const int ncw = w + 2 * K2_TPAD, nrw = h + 2 * K2_TPAD;
             auto stage_copy = [&](int kq) {   // one thread: residual box + tap rows of copy kq -> stage (k0+kq) % 4
@@ -542,7 +540,7 @@ k_gradient_update(const __grid_constant__ CUtensorMap rmap, const float* __restr
                 bulk_load(&S->ctap[0][0], tapc + ((slot0 + kq) * ncw + bq.cbx0 + K2_TPAD) * 4, K2_TAP_BYTES, bar);
                 bulk_load(&S->rtap[0][0], tapr + ((slot0 + kq) * nrw + bq.cby0 + K2_TPAD) * 4, K2_TAP_BYTES, bar);
             };
-            const bool issuer = lane == 0 && (K2Fill<TY, TWO>::producer ? is_producer : fw == 0);
+            const bool issuer = lane == 0 && (K2Fill<TY>::producer ? is_producer : fw == 0);
             int next_q = 0;   // issuer only: first copy of the chunk whose staging has not been issued yet
             if (issuer) for (; next_q < K2_AHEAD && next_q < nc; ++next_q) stage_copy(next_q);
             for (int kc = 0; kc < nc; ++kc) {
@@ -595,7 +593,7 @@ k_gradient_update(const __grid_constant__ CUtensorMap rmap, const float* __restr
         }
         return;
     }
-    if (K2Fill<TY, TWO>::reg_split) asm volatile("setmaxnreg.inc.sync.aligned.u32 88;");
+    if (TY == 64 && K2_REG_SPLIT) asm volatile("setmaxnreg.inc.sync.aligned.u32 88;");
 
     // the two pixels of a row (columns lane, lane+32) travel as the two lanes of packed fp32 registers
     const float X0f = (float)(tx0 + lane), X1f = (float)(tx0 + lane + 32);
@@ -1183,10 +1181,10 @@ static int configure_kernels() {
     if (!first_use_on_device(&done)) return ASR_OK;
     ASR_CUDA_TRY(cudaFuncSetAttribute(k_forward_residual<K1_XR_SMALL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k1_smem<K1_XR_SMALL>()));
     ASR_CUDA_TRY(cudaFuncSetAttribute(k_forward_residual<K1_XR_BIG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k1_smem<K1_XR_BIG>()));
-#define ASR_K2_ATTR(WG, BT, TY, TWO) \
-    ASR_CUDA_TRY(cudaFuncSetAttribute(k_gradient_update<WG, BT, TY, TWO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(k2_smem<TY>())));
-#define ASR_K2_ATTRS(TY, TWO) ASR_K2_ATTR(false, false, TY, TWO) ASR_K2_ATTR(false, true, TY, TWO) ASR_K2_ATTR(true, false, TY, TWO) ASR_K2_ATTR(true, true, TY, TWO)
-    ASR_K2_ATTRS(64, true) ASR_K2_ATTRS(32, false) ASR_K2_ATTRS(32, true)
+#define ASR_K2_ATTR(WG, BT, TY) \
+    ASR_CUDA_TRY(cudaFuncSetAttribute(k_gradient_update<WG, BT, TY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(k2_smem<TY>())));
+#define ASR_K2_ATTRS(TY) ASR_K2_ATTR(false, false, TY) ASR_K2_ATTR(false, true, TY) ASR_K2_ATTR(true, false, TY) ASR_K2_ATTR(true, true, TY)
+    ASR_K2_ATTRS(64) ASR_K2_ATTRS(32)
 #undef ASR_K2_ATTRS
 #undef ASR_K2_ATTR
     return ASR_OK;
@@ -1228,28 +1226,23 @@ extern "C" int asr_solve_workspace_bytes(int B, int N, int h, int w, int H, int 
 // image leaves most SMs idle and every CTA latency-bound; measured K2 104 -> 73 us per iteration with 32-row tiles and 8 fill
 // warps).  16-row tiles and four u buffers were measured too and never win.  ASR_K2_TY overrides the choice (tests, experiments).
 static int k2_tile_height(int n_images, int H, int W) {
-    if (const char* e = getenv("ASR_K2_TY")) { const int v = atoi(e); if (v == 64 || v == 32 || v == 33) return v; }
+    if (const char* e = getenv("ASR_K2_TY")) { const int v = atoi(e); if (v == 64 || v == 32) return v; }
     int n_sm = 148, dev = 0;
     if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
-    const long long tiles32 = (long long)n_images * ((W + K2_T - 1) / K2_T) * ((H + 31) / 32);
-    if (tiles32 <= n_sm) return 32;        // every 64x32 CTA gets an SM of its own: the latency variant
-    if (tiles32 <= 2LL * n_sm) return 33;  // 64x32 tiles, two CTAs per SM, all resident at once (two 512^2 images)
-    return 64;
+    const long long tiles32 = (long long)((W + K2_T - 1) / K2_T) * ((H + 31) / 32);
+    return (long long)n_images * tiles32 <= n_sm ? 32 : 64;   // the 32-row variant runs one CTA per SM
 }
-#define ASR_LAUNCH_K2_TY(WG, BT, TY, TWO, ntiles, nimg, st, ...) \
-    ASR_LAUNCH_TIMED(1, (k_gradient_update<WG, BT, TY, TWO>), dim3(ntiles, nimg), (K2Fill<TY, TWO>::threads), (k2_smem<TY>()), st, __VA_ARGS__)
+#define ASR_LAUNCH_K2_TY(WG, BT, TY, ntiles, nimg, st, ...) \
+    ASR_LAUNCH_TIMED(1, (k_gradient_update<WG, BT, TY>), dim3(ntiles, nimg), K2Fill<TY>::threads, (k2_smem<TY>()), st, __VA_ARGS__)
 #define ASR_LAUNCH_K2(WG, btv, ty, H, W, nimg, st, ...)                                                               \
     do {                                                                                                              \
-        const int rows_ = (ty) == 64 ? 64 : 32;   /* ty: 64, 32 (one CTA per SM) or 33 (32 rows, two CTAs per SM) */     \
-        const int ntiles_ = ((W + K2_T - 1) / K2_T) * ((H + rows_ - 1) / rows_);                                      \
+        const int ntiles_ = ((W + K2_T - 1) / K2_T) * ((H + (ty) - 1) / (ty));                                        \
         if (btv) {                                                                                                    \
-            if ((ty) == 64) ASR_LAUNCH_K2_TY(WG, true, 64, true, ntiles_, nimg, st, __VA_ARGS__);                     \
-            else if ((ty) == 33) ASR_LAUNCH_K2_TY(WG, true, 32, true, ntiles_, nimg, st, __VA_ARGS__);                \
-            else ASR_LAUNCH_K2_TY(WG, true, 32, false, ntiles_, nimg, st, __VA_ARGS__);                               \
+            if ((ty) == 64) ASR_LAUNCH_K2_TY(WG, true, 64, ntiles_, nimg, st, __VA_ARGS__);                           \
+            else ASR_LAUNCH_K2_TY(WG, true, 32, ntiles_, nimg, st, __VA_ARGS__);                                      \
         } else {                                                                                                      \
-            if ((ty) == 64) ASR_LAUNCH_K2_TY(WG, false, 64, true, ntiles_, nimg, st, __VA_ARGS__);                    \
-            else if ((ty) == 33) ASR_LAUNCH_K2_TY(WG, false, 32, true, ntiles_, nimg, st, __VA_ARGS__);               \
-            else ASR_LAUNCH_K2_TY(WG, false, 32, false, ntiles_, nimg, st, __VA_ARGS__);                              \
+            if ((ty) == 64) ASR_LAUNCH_K2_TY(WG, false, 64, ntiles_, nimg, st, __VA_ARGS__);                          \
+            else ASR_LAUNCH_K2_TY(WG, false, 32, ntiles_, nimg, st, __VA_ARGS__);                                     \
         }                                                                                                             \
     } while (0)
 
