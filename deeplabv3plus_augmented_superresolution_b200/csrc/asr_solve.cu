@@ -354,6 +354,9 @@ struct __align__(16) KBox {
     int inv_ncx;    // ceil(65536 / ncx) for the cell index split
     int pad;
 };
+// what a gather warp needs of a copy, in one 32-byte record (two LDS.128): the rotate coefficients it multiplies itself, the tap
+// address constant of either u buffer already in the denormal-float form tap_addr2 takes, and the skip flag
+struct __align__(16) KGather { float b0, b3, b2, b5, cstf0, cstf1; int skip, pad; };
 // Per-copy inputs of the fill, staged by async copies two copies ahead: the LR residual box (TMA tensor load,
 // cells outside the grid arrive as zeros) and the translate tap tables of the box's cell columns / rows.
 constexpr int K2_TPAD = 24;            // tap tables carry 24 cells of halo on both sides (boxes are <= 24 cells)
@@ -368,8 +371,8 @@ struct __align__(128) K2Stage {
 constexpr unsigned K2_RBOX_BYTES = sizeof(float) * K2_BC * K2_RW, K2_TAP_BYTES = sizeof(float4) * K2_BC * 2;
 template <int TY>
 constexpr size_t k2_smem() {
-    return sizeof(float) * 2 * K2_US * K2Rows<TY>::value + (sizeof(KBox) + sizeof(InvXf)) * K2_CHUNK + sizeof(K2Stage) * K2_STAGES +
-           sizeof(float2) * 2 * TY;
+    return sizeof(float) * 2 * K2_US * K2Rows<TY>::value + (sizeof(KBox) + sizeof(InvXf) + sizeof(KGather)) * K2_CHUNK +
+           sizeof(K2Stage) * K2_STAGES + sizeof(float2) * 2 * TY;
 }
 
 __device__ __forceinline__ void bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
@@ -479,7 +482,8 @@ k_gradient_update(const __grid_constant__ CUtensorMap rmap, const float* __restr
     K2Stage* stages = reinterpret_cast<K2Stage*>(ut + 2 * K2_US * K2_UR);  // [K2_STAGES]
     KBox* boxes = reinterpret_cast<KBox*>(stages + K2_STAGES);            // [K2_CHUNK]
     InvXf* xfs = reinterpret_cast<InvXf*>(boxes + K2_CHUNK);              // [K2_CHUNK]
-    float2* rowp = reinterpret_cast<float2*>(xfs + K2_CHUNK);             // [2][TY] (fl(b1*Y), fl(b4*Y)) of the tile's rows, per u buffer
+    KGather* gth = reinterpret_cast<KGather*>(xfs + K2_CHUNK);            // [K2_CHUNK]
+    float2* rowp = reinterpret_cast<float2*>(gth + K2_CHUNK);             // [2][TY] (fl(b1*Y), fl(b4*Y)) of the tile's rows, per u buffer
     __shared__ __align__(8) unsigned long long stage_bar[K2_STAGES], full_bar[2];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -635,6 +639,9 @@ k_gradient_update(const __grid_constant__ CUtensorMap rmap, const float* __restr
             bx.pad = 0;
             boxes[tid] = bx;
             xfs[tid] = T;
+            // byte address of tap (y0,x0) = 4*(y0*US + x0) + cst: box origin, buffer and tile address folded into cst
+            const int cst0 = 4 * bx.cst + (int)smem_u32(ut), cst1 = cst0 + 4 * (K2_US * K2_UR);
+            gth[tid] = KGather{T.b0, T.b3, T.b2, T.b5, denorm_int(cst0), denorm_int(cst1), skip, 0};
         }
         bar_sync(0, K2_PART);
 
@@ -644,17 +651,14 @@ k_gradient_update(const __grid_constant__ CUtensorMap rmap, const float* __restr
             K2_TR(0);
             mbar_wait(&full_bar[kc & 1], ((k0 + kc) >> 1) & 1);   // u tile of copy kc is complete (no rendezvous among the gather warps)
             K2_TR(1);
-            const KBox bx = boxes[kc];
-            if (!(bx.ncxy >> 16)) {
-                const InvXf T = xfs[kc];
-                // byte address of tap (y0,x0) = 4*(y0*US + x0) + cst: box origin, buffer and tile address folded into cst
-                int cst = 4 * (bx.cst + (kc & 1) * (K2_US * K2_UR)) + (int)smem_u32(ut);
-                asm volatile("" : "+r"(cst));   // opaque and ordered after the wait above: no tap load can be hoisted over it
-                const float cstf = denorm_int(cst);
+            const KGather Gk = gth[kc];
+            if (!Gk.skip) {
+                float cstf = (kc & 1) ? Gk.cstf1 : Gk.cstf0;
+                asm volatile("" : "+f"(cstf));   // opaque and ordered after the wait above: no tap load can be hoisted over it
                 const f32x2 cstd = pk(cstf, cstf);
-                const f32x2 b2p = pk(T.b2, T.b2), b5p = pk(T.b5, T.b5);
+                const f32x2 b2p = pk(Gk.b2, Gk.b2), b5p = pk(Gk.b5, Gk.b5);
                 // products stay scalar (a packed product feeding a packed sum would be contracted, asr_common.cuh)
-                const f32x2 axp = pk(fmul(T.b0, X0f), fmul(T.b0, X1f)), ayp = pk(fmul(T.b3, X0f), fmul(T.b3, X1f));
+                const f32x2 axp = pk(fmul(Gk.b0, X0f), fmul(Gk.b0, X1f)), ayp = pk(fmul(Gk.b3, X0f), fmul(Gk.b3, X1f));
 #pragma unroll
                 for (int r = 0; r < K2_ROWS; ++r) {
                     const float2 rp = rowp[(kc & 1) * TY + warp + K2_GW * r];   // row products, built by the fill warps
