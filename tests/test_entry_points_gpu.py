@@ -118,3 +118,40 @@ def test_test_sr_entry_point_with_stand_in_model(tmp_path, capsys):
     assert ious["aug"] > 0.9 and ious["max"] > 0.8 and ious["mean"] > 0.8
     with pytest.raises(SystemExit):
         T.main(["--image", img, "--gt", gtp])      # no upstream model given
+
+
+@pytest.mark.parametrize("mode", ["argmax", "slice_max"])
+def test_sweep_grid_equals_point_by_point(tmp_path, mode):
+    """sweep_script.run_grid (all hyper-parameter points in one pass, LR stacks shared) == the reference's one-point-per-run loop
+    (sweep_script.py:88-161) repeated for every point, including each point's own running optimizer step counter."""
+    from deeplabv3plus_augmented_superresolution_b200 import sweep_script as S
+    from deeplabv3plus_augmented_superresolution_b200.superresolution_scripts import superres_utils as SU
+    hw, num_aug = (32, 32), 6
+    d, gt, names = _write_dir(tmp_path, 4, mode, num_aug=num_aug, hw=hw, bad_at=1)
+    grid = [dict(num_iter=7, lambda_tv=0.3, lambda_L2=0.7), dict(num_iter=5, learning_rate=5e-4, amsgrad=True, lambda_tv=1.0),
+            dict(num_iter=9, optimizer="sgd", momentum=0.6, learning_rate=1e-4, lambda_tv=0.2, lambda_L2=0.3)]
+    got = S.run_grid(grid, d, gt, None, num_aug=num_aug, num_samples=None, class_id=8, th_factor=0.65, batch=2, img_size=(128, 128),
+                     feature_size=hw, verbose=False)
+    assert len(got) == 3
+    for cfg, g in zip(grid, got):
+        sr = S.build_solver(cfg, num_aug, hw, (128, 128))
+        acc = {k: [] for k in ("aug_iou_single", "aug_iou_multiple", "max_iou", "mean_iou")}
+        for path in SU.list_precomputed_data_paths(d, sort=True):
+            try:
+                cm, mm, ang, sh, name = SU.load_SR_data(path, num_aug=num_aug, global_normalize=True)
+            except Exception:
+                continue
+            true = utils.load_image(os.path.join(gt, f"{name}.png"), image_size=(128, 128), normalize=False, is_png=True, resize_method="nearest")
+            m = {k: SU.compute_SR(sr, cm, ang, sh, name, str(tmp_path / "out"), SR_type=k, max_masks=mm, class_id=8, th_factor=0.65)
+                 for k in ("aug", "max", "mean")}
+            acc["aug_iou_single"].append(utils.compute_IoU(true, m["aug"], img_size=(128, 128), class_id=8))
+            acc["aug_iou_multiple"].append(utils.compute_IoU(true, m["aug"], img_size=(128, 128), class_id=8, include_bg=True))
+            acc["max_iou"].append(utils.compute_IoU(true, m["max"], img_size=(128, 128), class_id=8))
+            acc["mean_iou"].append(utils.compute_IoU(true, m["mean"], img_size=(128, 128), class_id=8))
+        assert len(acc["max_iou"]) == 3
+        for k, v in acc.items():
+            assert g[k] == pytest.approx(float(np.mean(v)), abs=1e-12), (cfg, k)
+        assert np.isnan(g["standard_iou_single"])          # no standard masks given
+    one = S.run_point(grid[1], d, gt, None, num_aug=num_aug, num_samples=None, class_id=8, th_factor=0.65, batch=4, img_size=(128, 128),
+                      feature_size=hw, verbose=False)
+    assert one == pytest.approx(got[1], nan_ok=True)
