@@ -155,3 +155,35 @@ def test_sweep_grid_equals_point_by_point(tmp_path, mode):
     one = S.run_point(grid[1], d, gt, None, num_aug=num_aug, num_samples=None, class_id=8, th_factor=0.65, batch=4, img_size=(128, 128),
                       feature_size=hw, verbose=False)
     assert one == pytest.approx(got[1], nan_ok=True)
+
+
+def test_generate_then_solve_through_the_entry_points(tmp_path):
+    """generate_augmented_copies (stand-in model) -> hdf5 directory -> SR_single_class.run: the whole chain through the in-repo
+    counterparts of the reference's scripts, on a tiny synthetic VOC tree."""
+    from PIL import Image
+    from deeplabv3plus_augmented_superresolution_b200 import generate_augmented_copies as G, SR_single_class as E
+    from deeplabv3plus_augmented_superresolution_b200.synthetic import make_test_image
+    data = tmp_path / "data"
+    voc = data / "dataset_root" / "VOCdevkit" / "VOC2012"
+    (voc / "JPEGImages").mkdir(parents=True); (voc / "SegmentationClassAug").mkdir(); (data / "augmented_file_lists").mkdir()
+    names = ["2007_000027", "2007_000032", "2007_000033"]
+    for i, n in enumerate(names):
+        img, gt = make_test_image((128, 128), 8, seed=5 + i)
+        if i == 1:
+            gt = np.zeros_like(gt)                                   # class 8 absent: filtered out by filter_images_by_class
+        Image.fromarray((img * 255.0 + 0.5).astype(np.uint8), mode="RGB").save(str(voc / "JPEGImages" / f"{n}.jpg"), quality=100, subsampling=0)
+        Image.fromarray(gt[..., 0].astype(np.uint8), mode="L").save(str(voc / "SegmentationClassAug" / f"{n}.png"))
+    (data / "augmented_file_lists" / "valaug.txt").write_text("\n".join(reversed(names)) + "\n")
+    args = G.build_parser().parse_args(["--num_aug", "8", "--num_samples", "5", "--mode", "argmax", "--angle_max", "0.15", "--shift_max", "10",
+                                        "--use_validation", "--class_id", "8", "--data_dir", str(data)])
+    written = G.run(args, SyntheticSegmenter(21, 8), image_size=(128, 128), verbose=False)
+    assert [os.path.basename(w) for w in written] == ["2007_000027.hdf5", "2007_000033.hdf5"]      # sorted, class-filtered
+    f = hdf5_lite.File(written[0], "r")
+    assert f["class_masks"].shape == (8, 32, 32, 1) and f.attrs["mode"] == "argmax" and f.attrs["shift_max"] == 10 and f.attrs["filename"] == "2007_000027"
+    assert set(np.unique(f["class_masks"][:8])) <= {0.0, 8.0}
+    f.close()
+    avg = E.run(os.path.dirname(written[0]), str(voc / "SegmentationClassAug"), None, num_aug=8, num_samples=None, class_id=8, th_factor=0.65,
+                batch=2, img_size=(128, 128), feature_size=(32, 32), verbose=False, num_iter=40)
+    assert avg["images"] == 2 and avg["aug_single"] > 0.85 and avg["max"] > 0.7 and avg["mean"] > 0.7
+    with pytest.raises(SystemExit):
+        G.main(["--class_id", "8", "--data_dir", str(data)])        # no upstream model given
