@@ -99,8 +99,12 @@ constexpr int K1_PBS = K1_PC;          // p buffer stride 48: 3 rows = 144 = 16 
                                        // the second phase land on complementary bank sets (stride 49 collided on one bank: 2 wavefronts per load)
 constexpr int K1_XS = 96;              // TMA box width (floats): 62*sqrt(2)+2+3 < 96, multiple of 32 (a pitch of 80 = 16 mod 32 saves TMA
                                        // bytes for small rotations but adds conflicts across source rows: measured 29.5 vs 28.0 us)
-constexpr int K1_XR_SMALL = 76;        // TMA box height when 62|sin|+62|cos|+3 <= 76 for every copy (|angle| <~ 0.19 rad): 5 CTAs/SM
-constexpr int K1_XR_BIG = 92;          // ... for any rotation: 62*sqrt(2)+3 < 92: 4 CTAs/SM
+#ifndef ASR_K1_XR_SMALL
+#define ASR_K1_XR_SMALL 74
+#endif
+constexpr int K1_XR_SMALL = ASR_K1_XR_SMALL;   // TMA box height when 62|sin|+62|cos|+3.05 <= 74 for every copy (|angle| <= 0.15 rad, the reference's
+                                       // angle_max): 37.6 KB per CTA = 6 CTAs/SM, the register limit.  76 rows (|angle| <~ 0.19) was 5 CTAs/SM: 23.9 -> 22.8 us
+constexpr int K1_XR_BIG = 92;          // ... for any rotation: 62*sqrt(2)+3 < 92: 44.6 KB per CTA = 5 CTAs/SM
 constexpr int K1_SPAN_X = 4 * (K1_TJ - 1) + 2, K1_SPAN_Y = 4 * (K1_TI - 1) + 2;   // last needed p position = first + SPAN
 constexpr int K1_EMPTY = INT_MIN;      // BoxDesc.by0 of a (tile, copy) whose rotated image is all zero
 template <int XR>
@@ -198,7 +202,9 @@ k_forward_residual(const __grid_constant__ CUtensorMap xmap, const float* __rest
         const BoxDesc d = boxd[(size_t)slot * gridDim.x + blockIdx.x];
         boxs[0] = d.x; boxs[1] = d.y;
         mbar_init(&bar, 1);
+#ifndef ASR_K1_EXP_NOTMA   // experiment: no box load at all = the compute-only floor of this kernel (profiles/r02_k1_floors.txt)
         if (d.y != K1_EMPTY) tma_load_3d(xt, &xmap, d.x, d.y, b_base + b, &bar, (unsigned)(K1_XS * XR * sizeof(float)));
+#endif
     }
     const int ti = (ntj == 1) ? (int)blockIdx.x : (int)__umulhi(blockIdx.x, ntj_magic);          // tile row (2^32/1 does not fit the magic)
     const int tj = (int)blockIdx.x - ti * ntj;                                                    // tile column
@@ -232,11 +238,18 @@ k_forward_residual(const __grid_constant__ CUtensorMap xmap, const float* __rest
         const f32x2 axp = pk(ax, ax), ayp = pk(ay, ay), r2p = pk(T.r2, T.r2), r5p = pk(T.r5, T.r5);
         const f32x2 r1p = pk(T.r1, T.r1), r4p = pk(T.r4, T.r4), qy0p = pk(qy0, qy0);
         const f32x2 magic2 = pk(kMagic, kMagic), one2 = pk(1.0f, 1.0f);
+#ifndef ASR_K1_EXP_NOTMA
         mbar_wait(&bar, 0);
+#endif
         // two rows of the column travel as the two lanes of packed fp32 instructions (asr_common.cuh); the row
         // coordinates are small integers, so qy0 + offset is exact and equals the literal (float)qy
+#ifdef ASR_K1_EXP_NOGATHER   // experiment: descriptor + box load + stores only = the latency floor of one CTA per (tile, copy)
+#pragma unroll 1
+        for (int m = 0; m < 2; m += 2) {
+#else
 #pragma unroll
         for (int m = 0; m < 12; m += 2) {
+#endif
             const int o0 = 4 * (m / 3) + m % 3, o1 = 4 * ((m + 1) / 3) + (m + 1) % 3;
             const f32x2 qy2 = add2(qy0p, pk((float)o0, (float)o1));
             const f32x2 ix = add2(sum2(axp, mul2(r1p, qy2)), r2p);      // fl(fl(fl(r0*qx) + fl(r1*qy)) + r2)
@@ -1184,6 +1197,8 @@ static int configure_kernels() {
     static unsigned long long done = 0;   // one bit per device: the attribute belongs to the (function, device) pair
     if (!first_use_on_device(&done)) return ASR_OK;
     ASR_CUDA_TRY(cudaFuncSetAttribute(k_forward_residual<K1_XR_SMALL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k1_smem<K1_XR_SMALL>()));
+    ASR_CUDA_TRY(cudaFuncSetAttribute(k_forward_residual<K1_XR_SMALL>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));   // 6 CTAs need 227 of the 228 KB
+    ASR_CUDA_TRY(cudaFuncSetAttribute(k_forward_residual<K1_XR_BIG>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     ASR_CUDA_TRY(cudaFuncSetAttribute(k_forward_residual<K1_XR_BIG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k1_smem<K1_XR_BIG>()));
 #define ASR_K2_ATTR(WG, BT, TY) \
     ASR_CUDA_TRY(cudaFuncSetAttribute(k_gradient_update<WG, BT, TY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(k2_smem<TY>())));
