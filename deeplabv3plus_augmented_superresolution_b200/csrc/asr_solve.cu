@@ -175,6 +175,62 @@ __global__ void k_forward_tables(const FwdXf* __restrict__ fwd, const int* __res
     }
 }
 
+// The gather of one thread: p = rotate-gather of x at p column `pcn` of the tile, rows 12g..12g+11 (q rows qy0 + {0,1,2,4,5,6,8,9,10,12,13,14}),
+// from the source box at shared address `box` whose element (0,0) is image pixel (d.y, d.x).  Two rows travel as the two lanes of packed
+// fp32 instructions (asr_common.cuh); the row coordinates are small integers, so qy0 + offset is exact and equals the literal (float)qy.
+__device__ __forceinline__ void k1_gather(const FwdCopy& T, BoxDesc d, const float* box, float* prow, float qxf, float qy0) {
+    const float ax = fmul(T.r0, qxf), ay = fmul(T.r3, qxf);
+    // byte address of tap (y0,x0) = 4*(y0*XS + x0) + cst, box origin and tile address folded into cst
+    const int cst = (int)smem_u32(box) - 4 * (d.y * K1_XS + d.x);
+    const float cstf = denorm_int(cst);
+    const f32x2 cstd = pk(cstf, cstf);
+    const f32x2 axp = pk(ax, ax), ayp = pk(ay, ay), r2p = pk(T.r2, T.r2), r5p = pk(T.r5, T.r5);
+    const f32x2 r1p = pk(T.r1, T.r1), r4p = pk(T.r4, T.r4), qy0p = pk(qy0, qy0);
+    const f32x2 magic2 = pk(kMagic, kMagic), one2 = pk(1.0f, 1.0f);
+#ifdef ASR_K1_EXP_NOGATHER   // experiment: descriptor + box load + stores only = the latency floor of one CTA per (tile, copy)
+#pragma unroll 1
+    for (int m = 0; m < 2; m += 2) {
+#else
+#pragma unroll
+    for (int m = 0; m < 12; m += 2) {
+#endif
+        const int o0 = 4 * (m / 3) + m % 3, o1 = 4 * ((m + 1) / 3) + (m + 1) % 3;
+        const f32x2 qy2 = add2(qy0p, pk((float)o0, (float)o1));
+        const f32x2 ix = add2(sum2(axp, mul2(r1p, qy2)), r2p);      // fl(fl(fl(r0*qx) + fl(r1*qy)) + r2)
+        const f32x2 iy = add2(sum2(ayp, mul2(r4p, qy2)), r5p);
+        const f32x2 fxf = sub2(add2_rd(ix, magic2), magic2), fyf = sub2(add2_rd(iy, magic2), magic2);   // floors
+        // (x_ceil - x) == 1 - (x - x_floor) bit for bit unless x in (-1,0), where that weight only ever
+        // multiplies the out-of-image tap x_floor = -1, i.e. an exact zero
+        const f32x2 wx1 = sub2(ix, fxf), wx0 = sub2(one2, wx1);
+        const f32x2 wy1 = sub2(iy, fyf), wy0 = sub2(one2, wy1);
+        const f32x2 tp = tap_addr2<K1_XS>(fxf, fyf, cstd);
+        const unsigned ta = (unsigned)tp, tb = (unsigned)(tp >> 32);
+        const f32x2 o = bilerp2(pk(lds_tap<0>(ta), lds_tap<0>(tb)), pk(lds_tap<4>(ta), lds_tap<4>(tb)),
+                                pk(lds_tap<4 * K1_XS>(ta), lds_tap<4 * K1_XS>(tb)),
+                                pk(lds_tap<4 * K1_XS + 4>(ta), lds_tap<4 * K1_XS + 4>(tb)), wx0, wx1, wy0, wy1);
+        prow[m * K1_PBS] = pk_lo(o);
+        prow[(m + 1) * K1_PBS] = pk_hi(o);
+    }
+}
+
+// One LR cell: translate (2x2 z values from the cell's 3x3 p patch `pr`), resize (literal lerps at 0.5).
+__device__ __forceinline__ float k1_cell(const float* pr, float4 wc, float4 wr) {
+    float Tx[3][2];
+#pragma unroll
+    for (int bb = 0; bb < 3; ++bb) {
+        const float p0 = pr[bb * K1_PBS], p1 = pr[bb * K1_PBS + 1], p2 = pr[bb * K1_PBS + 2];
+        Tx[bb][0] = fadd(fmul(wc.x, p0), fmul(wc.y, p1));
+        Tx[bb][1] = fadd(fmul(wc.z, p1), fmul(wc.w, p2));
+    }
+    const float tl = fadd(fmul(wr.x, Tx[0][0]), fmul(wr.y, Tx[1][0]));
+    const float tr = fadd(fmul(wr.x, Tx[0][1]), fmul(wr.y, Tx[1][1]));
+    const float bl = fadd(fmul(wr.z, Tx[1][0]), fmul(wr.w, Tx[2][0]));
+    const float br = fadd(fmul(wr.z, Tx[1][1]), fmul(wr.w, Tx[2][1]));
+    const float top = fadd(tl, fmul(fsub(tr, tl), 0.5f));
+    const float bot = fadd(bl, fmul(fsub(br, bl), 0.5f));
+    return fadd(top, fmul(fsub(bot, top), 0.5f));
+}
+
 template <int XR>
 __global__ void __launch_bounds__(K1_THREADS)
 k_forward_residual(const __grid_constant__ CUtensorMap xmap, const float* __restrict__ copies, float* __restrict__ resid,
@@ -223,76 +279,28 @@ k_forward_residual(const __grid_constant__ CUtensorMap xmap, const float* __rest
         wr = __ldg(froww + (slot * (unsigned)h + (unsigned)i));
     }
     __syncthreads();   // box origin and barrier init visible
-    const bool empty = boxs[1] == K1_EMPTY;
+    const BoxDesc d = make_int2(boxs[0], boxs[1]);
+    const bool empty = d.y == K1_EMPTY;
 
     if (!empty && gathers) {
-        // ---- p = rotate-gather of x at the needed integer positions ------------------------------
-        const float qxf = (float)(qx_lo + pcn + pcn / 3);         // 4*(pcn/3) + pcn%3
-        const float qy0 = (float)(qy_lo + qrow0);                 // first row of the thread; rows qy0 + {0,1,2,4,5,6,8,9,10,12,13,14}
-        const float ax = fmul(T.r0, qxf), ay = fmul(T.r3, qxf);
-        // byte address of tap (y0,x0) = 4*(y0*XS + x0) + cst, box origin and tile address folded into cst
-        const int cst = (int)smem_u32(xt) - 4 * (boxs[1] * K1_XS + boxs[0]);
-        const float cstf = denorm_int(cst);
-        const f32x2 cstd = pk(cstf, cstf);
-        float* prow = pb + prow0 * K1_PBS + pcn;
-        const f32x2 axp = pk(ax, ax), ayp = pk(ay, ay), r2p = pk(T.r2, T.r2), r5p = pk(T.r5, T.r5);
-        const f32x2 r1p = pk(T.r1, T.r1), r4p = pk(T.r4, T.r4), qy0p = pk(qy0, qy0);
-        const f32x2 magic2 = pk(kMagic, kMagic), one2 = pk(1.0f, 1.0f);
 #ifndef ASR_K1_EXP_NOTMA
         mbar_wait(&bar, 0);
 #endif
-        // two rows of the column travel as the two lanes of packed fp32 instructions (asr_common.cuh); the row
-        // coordinates are small integers, so qy0 + offset is exact and equals the literal (float)qy
-#ifdef ASR_K1_EXP_NOGATHER   // experiment: descriptor + box load + stores only = the latency floor of one CTA per (tile, copy)
-#pragma unroll 1
-        for (int m = 0; m < 2; m += 2) {
-#else
-#pragma unroll
-        for (int m = 0; m < 12; m += 2) {
-#endif
-            const int o0 = 4 * (m / 3) + m % 3, o1 = 4 * ((m + 1) / 3) + (m + 1) % 3;
-            const f32x2 qy2 = add2(qy0p, pk((float)o0, (float)o1));
-            const f32x2 ix = add2(sum2(axp, mul2(r1p, qy2)), r2p);      // fl(fl(fl(r0*qx) + fl(r1*qy)) + r2)
-            const f32x2 iy = add2(sum2(ayp, mul2(r4p, qy2)), r5p);
-            const f32x2 fxf = sub2(add2_rd(ix, magic2), magic2), fyf = sub2(add2_rd(iy, magic2), magic2);   // floors
-            // (x_ceil - x) == 1 - (x - x_floor) bit for bit unless x in (-1,0), where that weight only ever
-            // multiplies the out-of-image tap x_floor = -1, i.e. an exact zero
-            const f32x2 wx1 = sub2(ix, fxf), wx0 = sub2(one2, wx1);
-            const f32x2 wy1 = sub2(iy, fyf), wy0 = sub2(one2, wy1);
-            const f32x2 tp = tap_addr2<K1_XS>(fxf, fyf, cstd);
-            const unsigned ta = (unsigned)tp, tb = (unsigned)(tp >> 32);
-            const f32x2 o = bilerp2(pk(lds_tap<0>(ta), lds_tap<0>(tb)), pk(lds_tap<4>(ta), lds_tap<4>(tb)),
-                                    pk(lds_tap<4 * K1_XS>(ta), lds_tap<4 * K1_XS>(tb)),
-                                    pk(lds_tap<4 * K1_XS + 4>(ta), lds_tap<4 * K1_XS + 4>(tb)), wx0, wx1, wy0, wy1);
-            prow[m * K1_PBS] = pk_lo(o);
-            prow[(m + 1) * K1_PBS] = pk_hi(o);
-        }
+        k1_gather(T, d, xt, pb + prow0 * K1_PBS + pcn, (float)(qx_lo + pcn + pcn / 3) /* 4*(pcn/3) + pcn%3 */, (float)(qy_lo + qrow0));
     }
     __syncthreads();
 
-    // ---- one cell per thread: translate (2x2 z values), resize (literal lerps at 0.5), minus y ---------
+    // ---- one cell per thread: translate, resize, minus y ---------
     if (live) {
-        float D = 0.0f;
-        if (!empty) {
-            float Tx[3][2];
-#pragma unroll
-            for (int bb = 0; bb < 3; ++bb) {
-                const float* pr = pb + (3 * ci + bb) * K1_PBS + 3 * cj;
-                const float p0 = pr[0], p1 = pr[1], p2 = pr[2];
-                Tx[bb][0] = fadd(fmul(wc.x, p0), fmul(wc.y, p1));
-                Tx[bb][1] = fadd(fmul(wc.z, p1), fmul(wc.w, p2));
-            }
-            const float tl = fadd(fmul(wr.x, Tx[0][0]), fmul(wr.y, Tx[1][0]));
-            const float tr = fadd(fmul(wr.x, Tx[0][1]), fmul(wr.y, Tx[1][1]));
-            const float bl = fadd(fmul(wr.z, Tx[1][0]), fmul(wr.w, Tx[2][0]));
-            const float br = fadd(fmul(wr.z, Tx[1][1]), fmul(wr.w, Tx[2][1]));
-            const float top = fadd(tl, fmul(fsub(tr, tl), 0.5f));
-            const float bot = fadd(bl, fmul(fsub(br, bl), 0.5f));
-            D = fadd(top, fmul(fsub(bot, top), 0.5f));
-        }
+        const float D = empty ? 0.0f : k1_cell(pb + 3 * ci * K1_PBS + 3 * cj, wc, wr);
         resid[(size_t)slot * (unsigned)(h * wp) + (unsigned)(i * wp + j)] = fsub(D, yk);
     }
 }
+
+// Measured and rejected (round 2, profiles/r02_k1_floors.txt): a pipelined form -- one CTA walks 10-20 consecutive copies of its tile with two
+// source boxes and two p buffers in rotation, next box and next operands in flight during the gather, one __syncthreads per copy.  It was
+// bit-identical and slower, 26.5 vs 22.6 us: two boxes per CTA leave 3 CTAs = 18 gather warps per SM, and the gather's dependent
+// coordinate -> floor -> address -> LDS -> lerp chain needs the 36 of the one-copy kernel more than it needs the hidden TMA latency.
 
 // ================================================================================================
 // K2: gradient + regularisers + optimizer step
