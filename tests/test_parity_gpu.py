@@ -84,6 +84,18 @@ def test_solve_bit_identical_to_oracle(case):
         assert_loss_close(float(loss[b]), lo)
 
 
+@pytest.mark.parametrize("amax", [0.15, 0.1501, 0.152, 0.19, 0.2])
+def test_forward_box_variant_boundary(amax):
+    """K1 stages a 74-row source box when every |angle| <= ~0.15 rad (the reference's ANGLE_MAX, test_SR.py:31) and a 92-row box otherwise;
+    a box that does not fit traps in k_forward_tables.  Copies at exactly +-amax, with shifts that push tiles over every canvas edge."""
+    N, h, w, iters = 6, 48, 32, 5
+    copies, ang, sh = synth(1, N, (h, w), amax, 60, seed=61)
+    ang = np.array([[amax, -amax, np.float32(amax), -np.float32(amax), 0.5 * amax, 0.0]], np.float32)
+    x = A.solve_batched(copies, ang, sh, A.SolveParams(num_iter=iters))
+    xo, _ = O.augmented_superresolution(copies[0].cpu().numpy(), ang[0], sh[0], O.SolveParams(num_iter=iters), output_size=(4 * h, 4 * w))
+    np.testing.assert_array_equal(x[0].cpu().numpy(), xo[..., 0])
+
+
 @pytest.mark.parametrize("ty", ["32", "64"])
 def test_both_gradient_tile_heights(ty, monkeypatch):
     """K2 runs 64x32 tiles for one or two images and 64x64 tiles otherwise; ASR_K2_TY forces either on the same input"""
