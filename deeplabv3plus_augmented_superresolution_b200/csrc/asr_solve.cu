@@ -301,6 +301,9 @@ k_forward_residual(const __grid_constant__ CUtensorMap xmap, const float* __rest
 // source boxes and two p buffers in rotation, next box and next operands in flight during the gather, one __syncthreads per copy.  It was
 // bit-identical and slower, 26.5 vs 22.6 us: two boxes per CTA leave 3 CTAs = 18 gather warps per SM, and the gather's dependent
 // coordinate -> floor -> address -> LDS -> lerp chain needs the 36 of the one-copy kernel more than it needs the hidden TMA latency.
+// A second form kept ONE box and one p buffer (still 6 CTAs/SM): an idle thread staged the next copy's record and box origin in shared memory
+// during the gather and the next box was requested right after the gather's barrier, so that its flight overlapped the cells.  22.4 vs 22.6 us
+// at 64 images, 23.7 vs 23.4 at 8: the six resident CTAs already hide each other's chains; not worth a second kernel.
 
 // ================================================================================================
 // K2: gradient + regularisers + optimizer step
