@@ -45,6 +45,7 @@ struct AsyncScratch {
 // our kernels ran in its timed region; with profiling on, the two solve kernels are bracketed by
 // CUDA events on the launching stream (summed by asr_profile_read after a stream sync).
 void count_launch();
+bool profile_enabled();    // asr_profile_enable(1): event records sit between the launches, so the solve launches without PDL
 void profile_mark(int slot, cudaStream_t st, bool begin);   // slot 0 = forward residual, 1 = gradient/update
 #define ASR_LAUNCH(kernel, grid, block, smem, st, ...)          \
     do {                                                        \
@@ -56,6 +57,31 @@ void profile_mark(int slot, cudaStream_t st, bool begin);   // slot 0 = forward 
         ::asr::profile_mark(slot, st, true);                       \
         ASR_LAUNCH(kernel, grid, block, smem, st, __VA_ARGS__);    \
         ::asr::profile_mark(slot, st, false);                      \
+    } while (0)
+
+// Programmatic dependent launch (the solve's K1 -> K2 -> K1 chain): with `pdl` set the kernel may be scheduled while the previous kernel
+// of the stream is still draining; it runs its own set-up and blocks in pdl_wait() until that kernel has completed and its writes are
+// visible.  Without the attribute (or after a non-kernel stream operation) pdl_wait() / pdl_trigger() are no-ops.
+template <typename... KArgs, typename... Args>
+inline void launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, bool pdl, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl ? 1 : 0;
+    count_launch();
+    cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+#define ASR_LAUNCH_TIMED_PDL(slot, pdl, kernel, grid, block, smem, st, ...)          \
+    do {                                                                             \
+        ::asr::profile_mark(slot, st, true);                                         \
+        ::asr::launch_pdl(kernel, grid, block, smem, st, pdl, __VA_ARGS__);          \
+        ::asr::profile_mark(slot, st, false);                                        \
     } while (0)
 
 // ---- exact fp32 building blocks ---------------------------------------------------------------
@@ -194,6 +220,9 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned pari
         "DONE_%=:\n"
         "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
 }
+// programmatic dependent launch, device side (see launch_pdl)
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }

@@ -81,6 +81,7 @@ struct OpenMark { int slot; cudaStream_t st; cudaEvent_t ev; };
 static std::vector<OpenMark> g_open;   // begin marks waiting for their end mark, keyed by (slot, stream)
 
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+bool profile_enabled() { return g_prof_on; }
 
 static cudaEvent_t take_event() {
     if (!g_pool.empty()) { cudaEvent_t e = g_pool.back(); g_pool.pop_back(); return e; }

@@ -258,6 +258,10 @@ k_forward_residual(const __grid_constant__ CUtensorMap xmap, const float* __rest
         const BoxDesc d = boxd[(size_t)slot * gridDim.x + blockIdx.x];
         boxs[0] = d.x; boxs[1] = d.y;
         mbar_init(&bar, 1);
+        // x is the previous kernel's output: everything above (and the operand loads of the other threads below) runs while that kernel
+        // drains; the next kernel of the chain may be scheduled as soon as every CTA of this grid is past this point
+        pdl_wait();
+        pdl_trigger();
 #ifndef ASR_K1_EXP_NOTMA   // experiment: no box load at all = the compute-only floor of this kernel (profiles/r02_k1_floors.txt)
         if (d.y != K1_EMPTY) tma_load_3d(xt, &xmap, d.x, d.y, b_base + b, &bar, (unsigned)(K1_XS * XR * sizeof(float)));
 #endif
@@ -278,6 +282,7 @@ k_forward_residual(const __grid_constant__ CUtensorMap xmap, const float* __rest
         wc = __ldg(fcolw + (slot * (unsigned)w + (unsigned)j));
         wr = __ldg(froww + (slot * (unsigned)h + (unsigned)i));
     }
+    pdl_wait();        // (returns at once for every thread but the first to ask; the residual stores below must not pass the previous kernel)
     __syncthreads();   // box origin and barrier init visible
     const BoxDesc d = make_int2(boxs[0], boxs[1]);
     const bool empty = d.y == K1_EMPTY;
@@ -570,7 +575,13 @@ k_gradient_update(const __grid_constant__ CUtensorMap rmap, const float* __restr
             };
             const bool issuer = lane == 0 && (K2Fill<TY>::producer ? is_producer : fw == 0);
             int next_q = 0;   // issuer only: first copy of the chunk whose staging has not been issued yet
-            if (issuer) for (; next_q < K2_AHEAD && next_q < nc; ++next_q) stage_copy(next_q);
+            if (issuer) {
+                if (k0 == 0) {   // the residual is the previous kernel's output; all set-up above overlapped its tail (launch_pdl)
+                    pdl_wait();
+                    pdl_trigger();
+                }
+                for (; next_q < K2_AHEAD && next_q < nc; ++next_q) stage_copy(next_q);
+            }
             for (int kc = 0; kc < nc; ++kc) {
                 const int ub = kc & 1, gk = k0 + kc;
                 const KBox bc = boxes[kc];
@@ -1262,25 +1273,36 @@ static int k2_tile_height(int n_images, int H, int W) {
     const long long tiles32 = (long long)((W + K2_T - 1) / K2_T) * ((H + 31) / 32);
     return (long long)n_images * tiles32 <= n_sm ? 32 : 64;   // the 32-row variant runs one CTA per SM
 }
-#define ASR_LAUNCH_K2_TY(WG, BT, TY, ntiles, nimg, st, ...) \
-    ASR_LAUNCH_TIMED(1, (k_gradient_update<WG, BT, TY>), dim3(ntiles, nimg), K2Fill<TY>::threads, (k2_smem<TY>()), st, __VA_ARGS__)
-#define ASR_LAUNCH_K2(WG, btv, ty, H, W, nimg, st, ...)                                                               \
+#define ASR_LAUNCH_K2_TY(WG, BT, TY, pdl, ntiles, nimg, st, ...) \
+    ASR_LAUNCH_TIMED_PDL(1, pdl, (k_gradient_update<WG, BT, TY>), dim3(ntiles, nimg), K2Fill<TY>::threads, (k2_smem<TY>()), st, __VA_ARGS__)
+#define ASR_LAUNCH_K2(WG, btv, ty, pdl, H, W, nimg, st, ...)                                                          \
     do {                                                                                                              \
         const int ntiles_ = ((W + K2_T - 1) / K2_T) * ((H + (ty) - 1) / (ty));                                        \
         if (btv) {                                                                                                    \
-            if ((ty) == 64) ASR_LAUNCH_K2_TY(WG, true, 64, ntiles_, nimg, st, __VA_ARGS__);                           \
-            else ASR_LAUNCH_K2_TY(WG, true, 32, ntiles_, nimg, st, __VA_ARGS__);                                      \
+            if ((ty) == 64) ASR_LAUNCH_K2_TY(WG, true, 64, pdl, ntiles_, nimg, st, __VA_ARGS__);                      \
+            else ASR_LAUNCH_K2_TY(WG, true, 32, pdl, ntiles_, nimg, st, __VA_ARGS__);                                 \
         } else {                                                                                                      \
-            if ((ty) == 64) ASR_LAUNCH_K2_TY(WG, false, 64, ntiles_, nimg, st, __VA_ARGS__);                          \
-            else ASR_LAUNCH_K2_TY(WG, false, 32, ntiles_, nimg, st, __VA_ARGS__);                                     \
+            if ((ty) == 64) ASR_LAUNCH_K2_TY(WG, false, 64, pdl, ntiles_, nimg, st, __VA_ARGS__);                     \
+            else ASR_LAUNCH_K2_TY(WG, false, 32, pdl, ntiles_, nimg, st, __VA_ARGS__);                                \
         }                                                                                                             \
     } while (0)
 
-#define ASR_LAUNCH_K1(small, t1, nk, nimg, st, ...)                                                                                     \
+#define ASR_LAUNCH_K1(small, pdl, t1, nk, nimg, st, ...)                                                                                \
     do {                                                                                                                                \
-        if (small) ASR_LAUNCH_TIMED(0, k_forward_residual<K1_XR_SMALL>, dim3(t1, nk, nimg), K1_THREADS, k1_smem<K1_XR_SMALL>(), st, __VA_ARGS__); \
-        else ASR_LAUNCH_TIMED(0, k_forward_residual<K1_XR_BIG>, dim3(t1, nk, nimg), K1_THREADS, k1_smem<K1_XR_BIG>(), st, __VA_ARGS__);           \
+        if (small) ASR_LAUNCH_TIMED_PDL(0, pdl, k_forward_residual<K1_XR_SMALL>, dim3(t1, nk, nimg), K1_THREADS, k1_smem<K1_XR_SMALL>(), st, __VA_ARGS__); \
+        else ASR_LAUNCH_TIMED_PDL(0, pdl, k_forward_residual<K1_XR_BIG>, dim3(t1, nk, nimg), K1_THREADS, k1_smem<K1_XR_BIG>(), st, __VA_ARGS__);           \
     } while (0)
+
+// Programmatic dependent launch inside the iteration loop (profiles/r02_pdl.txt).  K1 launches always overlap the previous K2's tail: the
+// descriptor / record / operand loads of its first wave run while K2 drains (-2.5 % per iteration for one image, never slower).  K2 launches
+// overlap the previous K1's tail only in the one-image variant (32-row tiles: every CTA needs a whole SM, so it cannot displace K1's CTAs):
+// another -3.7 % there, but with 64-row tiles and a grid of about one CTA per SM (two images) the early CTAs take half of every SM away
+// from K1 for most of its run: 136 -> 196 us per iteration.
+// ASR_PDL (experiments): bit 0 = K1 launches, bit 1 = K2 launches; default 3
+static int pdl_mask() {
+    static const int m = [] { const char* e = getenv("ASR_PDL"); return e ? atoi(e) : 3; }();
+    return m;
+}
 
 static int solve_impl(const AsrSolveParams* params, int n_params, const float* d_copies, const float* h_angles,
                       const float* h_shifts, const uint8_t* h_keep, const int32_t* h_stack_index, int B, int N, int h, int w,
@@ -1358,18 +1380,19 @@ static int solve_impl(const AsrSolveParams* params, int n_params, const float* d
         }
         return G;
     };
-    auto launch_k1 = [&](const Group& G, int it, cudaStream_t s) -> int {
+    // pdl: the launch directly follows the other solve kernel of the same group in the stream (no loss trace, no profile mark in between)
+    auto launch_k1 = [&](const Group& G, int it, cudaStream_t s, bool pdl) -> int {
         const size_t ro = (size_t)G.b0 * N * h * wp, so = (size_t)G.b0 * N;
-        ASR_LAUNCH_K1(T.small_box, t1, T.max_kept, G.nb, s, (it & 1) ? map_b : map_a, d_copies, D.resid + ro, D.fcp + so, D.fcolw + so * w,
+        ASR_LAUNCH_K1(T.small_box, pdl, t1, T.max_kept, G.nb, s, (it & 1) ? map_b : map_a, d_copies, D.resid + ro, D.fcp + so, D.fcolw + so * w,
                       D.froww + so * h, D.boxd + so * t1, D.ip + G.b0, it, (!G.uniform_kept || it >= G.min_iters) ? 1 : 0, N, h, w, wp, ntj,
                       div_magic(ntj), G.b0);
         return ASR_OK;
     };
-    auto launch_k2 = [&](const Group& G, int it, cudaStream_t s) -> int {
+    auto launch_k2 = [&](const Group& G, int it, cudaStream_t s, bool pdl) -> int {
         const size_t po = (size_t)G.b0 * plane;
         float* xc = ((it & 1) ? D.xb : D.xa) + po;
         float* xn = ((it & 1) ? D.xa : D.xb) + po;
-        ASR_LAUNCH_K2(false, T.any_btv, G.ty, H, W, G.nb, s, map_r, xc, xn, D.s0 + po, D.s1 + po, D.s2 + po, D.tapc, D.tapr,
+        ASR_LAUNCH_K2(false, T.any_btv, G.ty, pdl, H, W, G.nb, s, map_r, xc, xn, D.s0 + po, D.s1 + po, D.s2 + po, D.tapc, D.tapr,
                       D.inv + (size_t)G.b0 * N, D.ip + G.b0, D.sched + G.b0, it, N, h, w, H, W, B, G.b0);
         return ASR_OK;
     };
@@ -1377,13 +1400,15 @@ static int solve_impl(const AsrSolveParams* params, int n_params, const float* d
     // (Two halves of a group on two streams, half an iteration apart, so that K1 of one half shares the SMs with K2 of the other:
     //  measured +1.3 % with the kernels as they are and -16 % when K2 is held to one CTA per SM to make room -- both kernels are
     //  issue-heavy, there is little idle capacity to trade.  scripts/dev/dual_stream_experiment.sh, DESIGN.md.)
+    const int pdl = profile_enabled() ? 0 : pdl_mask();   // profile marks are event records between the launches
     for (int b0 = 0; b0 < B; b0 += group) {
         const int nb = (B - b0 < group) ? B - b0 : group;
         const Group G = make_group(b0, nb);
         for (int it = 0; it < G.iters; ++it) {
-            if (int e = launch_k1(G, it, st)) return e;
+            const bool traced = loss_every > 0 && it % loss_every == 0;   // a loss kernel sits between K1 and K2 of this iteration
+            if (int e = launch_k1(G, it, st, (pdl & 1) && it > 0)) return e;
             if (int e = trace_loss(b0, nb, it)) return e;
-            if (int e = launch_k2(G, it, st)) return e;
+            if (int e = launch_k2(G, it, st, (pdl & 2) && G.ty == 32 && !traced)) return e;
         }
     }
     ASR_CUDA_TRY(cudaGetLastError());
@@ -1461,9 +1486,9 @@ extern "C" int asr_loss_grad_batched(const AsrSolveParams* params, int n_params,
     ASR_LAUNCH(k_tap_tables, dim3((4 * (w + h + 4 * K2_TPAD) + 255) / 256, N, B), 256, 0, st, D.inv, D.tapc, D.tapr, N, h, w, H, W);
     ASR_LAUNCH(k_forward_tables, dim3((t1 + w + h + 127) / 128, T.max_kept, B), 128, 0, st, D.fwd, D.src, D.ip, D.fcp, D.fcolw, D.froww,
                D.boxd, N, h, w, H, W, ntj, nti, box_rows);
-    ASR_LAUNCH_K1(T.small_box, t1, T.max_kept, B, st, map_a, d_copies, D.resid, D.fcp, D.fcolw, D.froww, D.boxd, D.ip, 0, 1, N, h, w, wp, ntj,
+    ASR_LAUNCH_K1(T.small_box, false, t1, T.max_kept, B, st, map_a, d_copies, D.resid, D.fcp, D.fcolw, D.froww, D.boxd, D.ip, 0, 1, N, h, w, wp, ntj,
                   div_magic(ntj), 0);
-    ASR_LAUNCH_K2(true, T.any_btv, k2_tile_height(B, H, W), H, W, B, st, map_r, D.xa, D.xb, D.s0, D.s1, D.s2, D.tapc, D.tapr, D.inv, D.ip,
+    ASR_LAUNCH_K2(true, T.any_btv, k2_tile_height(B, H, W), false, H, W, B, st, map_r, D.xa, D.xb, D.s0, D.s1, D.s2, D.tapc, D.tapr, D.inv, D.ip,
                   D.sched, 0, N, h, w, H, W, B, 0);
     }
     ASR_CUDA_TRY(cudaGetLastError());
