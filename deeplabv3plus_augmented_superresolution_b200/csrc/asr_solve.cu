@@ -235,10 +235,11 @@ template <int XR>
 __global__ void __launch_bounds__(K1_THREADS)
 k_forward_residual(const __grid_constant__ CUtensorMap xmap, const float* __restrict__ copies, float* __restrict__ resid,
                    const FwdCopy* __restrict__ fcp, const float4* __restrict__ fcolw, const float4* __restrict__ froww,
-                   const BoxDesc* __restrict__ boxd, const ImgParams* __restrict__ ip, int it, int check_ip, int N, int h, int w, int wp,
+                   const BoxDesc* __restrict__ boxd, const ImgParams* __restrict__ ip, int it, int flags, int N, int h, int w, int wp,
                    int ntj, unsigned ntj_magic, int b_base) {
     const int b = blockIdx.z, ks = blockIdx.y;
-    if (check_ip && (ks >= ip[b].n_kept || it >= ip[b].num_iter)) return;   // host clears check_ip when every image of the launch is live
+    // flags: bit 0 = look at ImgParams (the host clears it when every image of the launch is live), bit 1 = let the next kernel in early
+    if ((flags & 1) && (ks >= ip[b].n_kept || it >= ip[b].num_iter)) return;
 
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ __align__(8) unsigned long long bar;
@@ -261,7 +262,7 @@ k_forward_residual(const __grid_constant__ CUtensorMap xmap, const float* __rest
         // x is the previous kernel's output: everything above (and the operand loads of the other threads below) runs while that kernel
         // drains; the next kernel of the chain may be scheduled as soon as every CTA of this grid is past this point
         pdl_wait();
-        pdl_trigger();
+        if (flags & 2) pdl_trigger();   // else the next kernel is let in when this grid's CTAs exit
 #ifndef ASR_K1_EXP_NOTMA   // experiment: no box load at all = the compute-only floor of this kernel (profiles/r02_k1_floors.txt)
         if (d.y != K1_EMPTY) tma_load_3d(xt, &xmap, d.x, d.y, b_base + b, &bar, (unsigned)(K1_XS * XR * sizeof(float)));
 #endif
@@ -1293,11 +1294,12 @@ static int k2_tile_height(int n_images, int H, int W) {
         else ASR_LAUNCH_TIMED_PDL(0, pdl, k_forward_residual<K1_XR_BIG>, dim3(t1, nk, nimg), K1_THREADS, k1_smem<K1_XR_BIG>(), st, __VA_ARGS__);           \
     } while (0)
 
-// Programmatic dependent launch inside the iteration loop (profiles/r02_pdl.txt).  K1 launches always overlap the previous K2's tail: the
-// descriptor / record / operand loads of its first wave run while K2 drains (-2.5 % per iteration for one image, never slower).  K2 launches
-// overlap the previous K1's tail only in the one-image variant (32-row tiles: every CTA needs a whole SM, so it cannot displace K1's CTAs):
-// another -3.7 % there, but with 64-row tiles and a grid of about one CTA per SM (two images) the early CTAs take half of every SM away
-// from K1 for most of its run: 136 -> 196 us per iteration.
+// Programmatic dependent launch inside the iteration loop (profiles/r02_pdl.txt).  Every K1 launch may overlap the previous K2's tail and
+// every K2 launch the previous K1's: the set-up of the first wave (descriptor, record and operand loads; chunk prologue, barrier set-up,
+// L2 prefetch) runs while the other kernel drains.  K2 lets K1 in right after its own wait.  K1 does that only in the one-image variant
+// (32-row K2 tiles: a K2 CTA needs a whole SM and cannot displace K1's CTAs); otherwise K2 is let in when K1's CTAs exit -- with an early
+// trigger the 64-row K2 CTAs of a two-image solve became resident at once and held half of every SM while K1 still had most of its
+// grid to run: 136 -> 196 us per iteration.  One image -5.9 % per iteration, 2..8 images -3.5..-0.9 %, 64 images +-0; never slower.
 // ASR_PDL (experiments): bit 0 = K1 launches, bit 1 = K2 launches; default 3
 static int pdl_mask() {
     static const int m = [] { const char* e = getenv("ASR_PDL"); return e ? atoi(e) : 3; }();
@@ -1384,7 +1386,7 @@ static int solve_impl(const AsrSolveParams* params, int n_params, const float* d
     auto launch_k1 = [&](const Group& G, int it, cudaStream_t s, bool pdl) -> int {
         const size_t ro = (size_t)G.b0 * N * h * wp, so = (size_t)G.b0 * N;
         ASR_LAUNCH_K1(T.small_box, pdl, t1, T.max_kept, G.nb, s, (it & 1) ? map_b : map_a, d_copies, D.resid + ro, D.fcp + so, D.fcolw + so * w,
-                      D.froww + so * h, D.boxd + so * t1, D.ip + G.b0, it, (!G.uniform_kept || it >= G.min_iters) ? 1 : 0, N, h, w, wp, ntj,
+                      D.froww + so * h, D.boxd + so * t1, D.ip + G.b0, it, ((!G.uniform_kept || it >= G.min_iters) ? 1 : 0) | (G.ty == 32 ? 2 : 0), N, h, w, wp, ntj,
                       div_magic(ntj), G.b0);
         return ASR_OK;
     };
@@ -1408,7 +1410,7 @@ static int solve_impl(const AsrSolveParams* params, int n_params, const float* d
             const bool traced = loss_every > 0 && it % loss_every == 0;   // a loss kernel sits between K1 and K2 of this iteration
             if (int e = launch_k1(G, it, st, (pdl & 1) && it > 0)) return e;
             if (int e = trace_loss(b0, nb, it)) return e;
-            if (int e = launch_k2(G, it, st, (pdl & 2) && G.ty == 32 && !traced)) return e;
+            if (int e = launch_k2(G, it, st, (pdl & 2) && !traced)) return e;
         }
     }
     ASR_CUDA_TRY(cudaGetLastError());
