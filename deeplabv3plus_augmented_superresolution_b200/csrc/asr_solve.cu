@@ -552,6 +552,13 @@ k_gradient_update(const __grid_constant__ CUtensorMap rmap, const float* __restr
     if (!gather_role) {
         if (TY == 64 && K2_REG_SPLIT) asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");   // every warp of both warpgroups, same instruction
         if (tid >= K2_PART) return;   // warps beyond the fill warps and the producer only exist to make whole warpgroups
+        // The residual is the previous kernel's output and only the staging thread touches it (through TMA): it waits here, while the gather
+        // warps build the first chunk's boxes, and lets the next kernel in.  (Kept out of the chunk loop: inside it the staging path lost
+        // its uniform-register address arithmetic and K2 ran 3 % slower.)
+        if (lane == 0 && warp - K2_GW == (K2Fill<TY>::producer ? K2Fill<TY>::fillers : 0)) {
+            pdl_wait();
+            pdl_trigger();
+        }
         for (int k0 = 0; k0 < nk; k0 += K2_CHUNK) {
             const int nc = min(K2_CHUNK, nk - k0);
             bar_sync(0, K2_PART);   // the previous chunk's boxes are no longer read
@@ -576,13 +583,7 @@ k_gradient_update(const __grid_constant__ CUtensorMap rmap, const float* __restr
             };
             const bool issuer = lane == 0 && (K2Fill<TY>::producer ? is_producer : fw == 0);
             int next_q = 0;   // issuer only: first copy of the chunk whose staging has not been issued yet
-            if (issuer) {
-                if (k0 == 0) {   // the residual is the previous kernel's output; all set-up above overlapped its tail (launch_pdl)
-                    pdl_wait();
-                    pdl_trigger();
-                }
-                for (; next_q < K2_AHEAD && next_q < nc; ++next_q) stage_copy(next_q);
-            }
+            if (issuer) for (; next_q < K2_AHEAD && next_q < nc; ++next_q) stage_copy(next_q);
             for (int kc = 0; kc < nc; ++kc) {
                 const int ub = kc & 1, gk = k0 + kc;
                 const KBox bc = boxes[kc];
@@ -1299,7 +1300,7 @@ static int k2_tile_height(int n_images, int H, int W) {
 // L2 prefetch) runs while the other kernel drains.  K2 lets K1 in right after its own wait.  K1 does that only in the one-image variant
 // (32-row K2 tiles: a K2 CTA needs a whole SM and cannot displace K1's CTAs); otherwise K2 is let in when K1's CTAs exit -- with an early
 // trigger the 64-row K2 CTAs of a two-image solve became resident at once and held half of every SM while K1 still had most of its
-// grid to run: 136 -> 196 us per iteration.  One image -5.9 % per iteration, 2..8 images -3.5..-0.9 %, 64 images +-0; never slower.
+// grid to run: 136 -> 196 us per iteration.  One image -5.7 % per iteration, 2..8 images -3.6..-1.2 %, 64 images +-0; never slower.
 // ASR_PDL (experiments): bit 0 = K1 launches, bit 1 = K2 launches; default 3
 static int pdl_mask() {
     static const int m = [] { const char* e = getenv("ASR_PDL"); return e ? atoi(e) : 3; }();
