@@ -1303,8 +1303,8 @@ static int k2_tile_height(int n_images, int H, int W) {
 // grid to run: 136 -> 196 us per iteration.  One image -5.7 % per iteration, 2..8 images -3.6..-1.2 %, 64 images +-0; never slower.
 // ASR_PDL (experiments): bit 0 = K1 launches, bit 1 = K2 launches; default 3
 static int pdl_mask() {
-    static const int m = [] { const char* e = getenv("ASR_PDL"); return e ? atoi(e) : 3; }();
-    return m;
+    const char* e = getenv("ASR_PDL");   // read per solve, like ASR_K2_TY: tests switch it inside one process
+    return e ? atoi(e) : 3;
 }
 
 static int solve_impl(const AsrSolveParams* params, int n_params, const float* d_copies, const float* h_angles,

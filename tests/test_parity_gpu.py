@@ -96,6 +96,27 @@ def test_forward_box_variant_boundary(amax):
     np.testing.assert_array_equal(x[0].cpu().numpy(), xo[..., 0])
 
 
+@pytest.mark.parametrize("B", [1, 6])   # 32-row gradient tiles (K1 lets K2 in early) and 64-row tiles
+def test_launch_chaining_modes_are_identical(B, monkeypatch):
+    """The two solve kernels are chained with programmatic dependent launch (ASR_PDL bit 0: forward-residual launches, bit 1: gradient
+    launches).  Every mode must give the bits of the plain launches, with and without a loss trace between the kernels; a missing wait
+    would show up as a race between one kernel's tail and the next one's first wave."""
+    copies, ang, sh = synth(B, 24, (64, 64), 0.15, 40, seed=71)
+    outs = {}
+    for mask in ("0", "1", "2", "3"):
+        monkeypatch.setenv("ASR_PDL", mask)
+        for rep in range(2):
+            x = A.solve_batched(copies, ang, sh, A.SolveParams(num_iter=40))
+            xt, _, trace = A.solve_batched(copies, ang, sh, A.SolveParams(num_iter=40), want_loss=True, loss_every=10)
+            outs[(mask, rep)] = (x.cpu().numpy(), xt.cpu().numpy(), trace.cpu().numpy())
+    ref = outs[("0", 0)]
+    for key, got in outs.items():
+        for a, b in zip(ref, got):
+            np.testing.assert_array_equal(a, b, err_msg=f"ASR_PDL={key[0]} repetition {key[1]}")
+    xo, _ = O.augmented_superresolution(copies[0].cpu().numpy(), ang[0], sh[0], O.SolveParams(num_iter=40), output_size=(256, 256))
+    np.testing.assert_array_equal(ref[0][0], xo[..., 0])
+
+
 @pytest.mark.parametrize("ty", ["32", "64"])
 def test_both_gradient_tile_heights(ty, monkeypatch):
     """K2 runs 64x32 tiles for one or two images and 64x64 tiles otherwise; ASR_K2_TY forces either on the same input"""
